@@ -1,0 +1,197 @@
+// crb_ekf.cu — batched EKF localisation step for sm_100a.
+//
+// Replaces ekf_estimation() of the reference, src/extended_kalman_filter.cpp:64-78, together with
+// motion_model :22-36, jacobF :38-47, observation_model :50-55 and jacobH :57-62, for n independent
+// agents per launch.
+//
+// Mapping: ONE THREAD PER AGENT.  The filter is a pure streaming op (176 algorithmic bytes and
+// ~250 flops per update): the roofline is HBM, so what matters is that every warp-level access is
+// one fully used 128-byte line.  All arrays are SoA field-major (field f of agent i at f*ld + i),
+// so lane l of a warp reads consecutive floats of one field; the 24 loads of an agent are issued
+// back to back (independent, ~96 B in flight per thread) and the 4x4 algebra lives in registers.
+//
+// Arithmetic: the kernel reproduces the dense Eigen evaluation of the reference entry for entry.
+// jF is identity plus four entries and jH is a row selector; multiplying by an exact 0/1 and adding
+// an exact 0 is exact in IEEE arithmetic, so only the non-trivial terms are evaluated, in the same
+// (sequential-k) order and with separate multiply and add (this TU is compiled with -fmad=false; the
+// kernel is memory-bound, FMUL+FADD instead of FFMA costs nothing).  With that, results differ from
+// the CPU restatement only through sinf/cosf (CUDA vs glibc, <= 2 ulp).
+#include "crb_common.cuh"
+
+struct EkfArgs {
+  double dt;
+  float Q[16];
+  float R[4];
+};
+
+// One filter step on register state.  P is column-major: P[r + 4*c].
+__device__ __forceinline__ void ekf_step(float (&x)[4], float (&P)[16], float z0, float z1,
+                                         float u0, float u1, const EkfArgs& a) {
+  // ---- motion_model(xEst, u) :22-36.  B_(0,0) = DT*cos(yaw) is a double product narrowed to float.
+  float s, c;
+  sincosf(x[2], &s, &c);
+  const float b00 = (float)(a.dt * (double)c);
+  const float b10 = (float)(a.dt * (double)s);
+  const float b21 = (float)a.dt;
+  float xp[4];
+  xp[0] = x[0] + b00 * u0;
+  xp[1] = x[1] + b10 * u0;
+  xp[2] = x[2] + b21 * u1;
+  xp[3] = x[3] + u0;  // F_(3,3) = 1 and B_(3,0) = 1: v accumulates (reference quirk)
+
+  // ---- jacobF(xPred, u) :38-47: evaluated at the PREDICTED yaw with v = u(0).
+  float s2, c2;
+  sincosf(xp[2], &s2, &c2);
+  const float j02 = (float)((-a.dt * (double)u0) * (double)s2);
+  const float j03 = (float)(a.dt * (double)c2);
+  const float j12 = (float)((a.dt * (double)u0) * (double)c2);
+  const float j13 = (float)(a.dt * (double)s2);
+
+  // ---- PPred = (jF*P)*jF^T + Q :69.
+  // T = jF*P: rows 2,3 are rows of P; row 0 = (P0j + j02*P2j) + j03*P3j; row 1 likewise.
+  float T[16];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    T[0 + 4 * j] = (P[0 + 4 * j] + j02 * P[2 + 4 * j]) + j03 * P[3 + 4 * j];
+    T[1 + 4 * j] = (P[1 + 4 * j] + j12 * P[2 + 4 * j]) + j13 * P[3 + 4 * j];
+    T[2 + 4 * j] = P[2 + 4 * j];
+    T[3 + 4 * j] = P[3 + 4 * j];
+  }
+  // PP = T*jF^T + Q: columns 2,3 are columns of T; column 0 = (Ti0 + Ti2*j02) + Ti3*j03.
+  float PP[16];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    PP[i + 4 * 0] = ((T[i + 4 * 0] + T[i + 4 * 2] * j02) + T[i + 4 * 3] * j03) + a.Q[i + 4 * 0];
+    PP[i + 4 * 1] = ((T[i + 4 * 1] + T[i + 4 * 2] * j12) + T[i + 4 * 3] * j13) + a.Q[i + 4 * 1];
+    PP[i + 4 * 2] = T[i + 4 * 2] + a.Q[i + 4 * 2];
+    PP[i + 4 * 3] = T[i + 4 * 3] + a.Q[i + 4 * 3];
+  }
+
+  // ---- update :71-77.  zPred = xPred.xy; S = PPred[0:2,0:2] + R; closed-form 2x2 inverse.
+  const float y0 = z0 - xp[0];
+  const float y1 = z1 - xp[1];
+  const float S00 = PP[0] + a.R[0], S10 = PP[1] + a.R[1];
+  const float S01 = PP[4] + a.R[2], S11 = PP[5] + a.R[3];
+  const float det = S00 * S11 - S10 * S01;
+  const float invdet = 1.0f / det;
+  const float i00 = S11 * invdet, i10 = -S10 * invdet;
+  const float i01 = -S01 * invdet, i11 = S00 * invdet;
+  float K0[4], K1[4];  // K = (PPred*jH^T) * S^-1, columns 0 and 1
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    K0[i] = PP[i] * i00 + PP[i + 4] * i10;
+    K1[i] = PP[i] * i01 + PP[i + 4] * i11;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) x[i] = xp[i] + (K0[i] * y0 + K1[i] * y1);
+  // PEst = (I - K*jH)*PPred: M = I - K*jH has columns (e0-K0, e1-K1, e2, e3).
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float p0 = PP[0 + 4 * j], p1 = PP[1 + 4 * j];
+    P[0 + 4 * j] = (1.0f - K0[0]) * p0 + (0.0f - K1[0]) * p1;
+    P[1 + 4 * j] = (0.0f - K0[1]) * p0 + (1.0f - K1[1]) * p1;
+    P[2 + 4 * j] = ((0.0f - K0[2]) * p0 + (0.0f - K1[2]) * p1) + PP[2 + 4 * j];
+    P[3 + 4 * j] = ((0.0f - K0[3]) * p0 + (0.0f - K1[3]) * p1) + PP[3 + 4 * j];
+  }
+}
+
+// count agents, leading dimension ld (>= count) for x/P, ld_zu for z/u (they may live in a staging
+// buffer with a different pitch).
+__global__ void __launch_bounds__(256)
+crb_ekf_step_kernel(int64_t count, int64_t ld, float* __restrict__ x, float* __restrict__ P,
+                    const float* __restrict__ z, const float* __restrict__ u, int64_t ld_zu,
+                    int n_steps, EkfArgs a) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float xs[4], Ps[16];
+#pragma unroll
+  for (int f = 0; f < 4; ++f) xs[f] = ld_stream(x + f * ld + i);
+#pragma unroll
+  for (int f = 0; f < 16; ++f) Ps[f] = ld_stream(P + f * ld + i);
+  float z0 = ld_stream(z + 0 * ld_zu + i), z1 = ld_stream(z + 1 * ld_zu + i);
+  float u0 = ld_stream(u + 0 * ld_zu + i), u1 = ld_stream(u + 1 * ld_zu + i);
+  for (int s = 0; s < n_steps; ++s) {
+    float nz0 = 0.f, nz1 = 0.f, nu0 = 0.f, nu1 = 0.f;
+    if (s + 1 < n_steps) {  // prefetch the next step's observation/control under this step's math
+      const int64_t o = (int64_t)(s + 1) * 2;
+      nz0 = ld_stream(z + (o + 0) * ld_zu + i);
+      nz1 = ld_stream(z + (o + 1) * ld_zu + i);
+      nu0 = ld_stream(u + (o + 0) * ld_zu + i);
+      nu1 = ld_stream(u + (o + 1) * ld_zu + i);
+    }
+    ekf_step(xs, Ps, z0, z1, u0, u1, a);
+    z0 = nz0; z1 = nz1; u0 = nu0; u1 = nu1;
+  }
+#pragma unroll
+  for (int f = 0; f < 4; ++f) st_stream(x + f * ld + i, xs[f]);
+#pragma unroll
+  for (int f = 0; f < 16; ++f) st_stream(P + f * ld + i, Ps[f]);
+}
+
+static int ekf_launch(crb_ctx* ctx, cudaStream_t st, int64_t count, int64_t ld, float* x, float* P,
+                      const float* z, const float* u, int64_t ld_zu, int n_steps,
+                      const crb_ekf_params* prm) {
+  EkfArgs a;
+  a.dt = prm->dt;
+  memcpy(a.Q, prm->Q, sizeof(a.Q));
+  memcpy(a.R, prm->R, sizeof(a.R));
+  const int block = 256;
+  crb_ekf_step_kernel<<<crb_grid_for(count, block), block, 0, st>>>(count, ld, x, P, z, u, ld_zu,
+                                                                    n_steps, a);
+  CRB_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return CRB_OK;
+}
+
+extern "C" int crb_ekf_step_batched(crb_ctx* ctx, int64_t n, float* x, float* P, const float* z,
+                                    const float* u, const crb_ekf_params* prm, int n_steps) {
+  CRB_REQUIRE(ctx != nullptr, "ctx is NULL");
+  CRB_REQUIRE(n >= 0 && n_steps >= 1, "n < 0 or n_steps < 1");
+  CRB_REQUIRE(prm != nullptr, "prm is NULL");
+  if (n == 0) return CRB_OK;
+  CRB_REQUIRE(x && P && z && u, "NULL array");
+  return ekf_launch(ctx, ctx->stream, n, n, x, P, z, u, n, n_steps, prm);
+}
+
+// Host-pointer variant: chunks of agents stream through CRB_N_PIPE staging arenas, each on its own
+// stream (H2D chunk k+1 and D2H chunk k-1 overlap the kernel of chunk k: both copy engines busy).
+extern "C" int crb_ekf_step_batched_host(crb_ctx* ctx, int64_t n, float* x, float* P,
+                                         const float* z, const float* u,
+                                         const crb_ekf_params* prm, int n_steps) {
+  CRB_REQUIRE(ctx != nullptr, "ctx is NULL");
+  CRB_REQUIRE(n >= 0 && n_steps >= 1, "n < 0 or n_steps < 1");
+  CRB_REQUIRE(prm != nullptr, "prm is NULL");
+  if (n == 0) return CRB_OK;
+  CRB_REQUIRE(x && P && z && u, "NULL array");
+  CRB_CUDA(cudaSetDevice(ctx->device));
+  const int64_t chunk_cap = n < (int64_t)131072 ? n : (int64_t)131072;
+  const size_t nf = 20 + (size_t)4 * n_steps;  // x4 P16 z2s u2s
+  const size_t pitch = (size_t)chunk_cap * sizeof(float);
+  for (int s = 0; s < CRB_N_PIPE; ++s) {
+    int rc = crb_ctx_pipe_reserve(ctx, s, nf * pitch);
+    if (rc) return rc;
+  }
+  const size_t hp = (size_t)n * sizeof(float);
+  int slot = 0;
+  for (int64_t i0 = 0; i0 < n; i0 += chunk_cap, slot = (slot + 1) % CRB_N_PIPE) {
+    const int64_t cnt = (n - i0) < chunk_cap ? (n - i0) : chunk_cap;
+    cudaStream_t st = ctx->pipe_stream[slot];
+    float* dx = (float*)ctx->pipe_buf[slot];
+    float* dP = dx + 4 * chunk_cap;
+    float* dz = dP + 16 * chunk_cap;
+    float* du = dz + (size_t)2 * n_steps * chunk_cap;
+    const size_t w = (size_t)cnt * sizeof(float);
+    CRB_CUDA(cudaMemcpy2DAsync(dx, pitch, x + i0, hp, w, 4, cudaMemcpyHostToDevice, st));
+    CRB_CUDA(cudaMemcpy2DAsync(dP, pitch, P + i0, hp, w, 16, cudaMemcpyHostToDevice, st));
+    CRB_CUDA(cudaMemcpy2DAsync(dz, pitch, z + i0, hp, w, (size_t)2 * n_steps,
+                               cudaMemcpyHostToDevice, st));
+    CRB_CUDA(cudaMemcpy2DAsync(du, pitch, u + i0, hp, w, (size_t)2 * n_steps,
+                               cudaMemcpyHostToDevice, st));
+    int rc = ekf_launch(ctx, st, cnt, chunk_cap, dx, dP, dz, du, chunk_cap, n_steps, prm);
+    if (rc) return rc;
+    CRB_CUDA(cudaMemcpy2DAsync(x + i0, hp, dx, pitch, w, 4, cudaMemcpyDeviceToHost, st));
+    CRB_CUDA(cudaMemcpy2DAsync(P + i0, hp, dP, pitch, w, 16, cudaMemcpyDeviceToHost, st));
+  }
+  for (int s = 0; s < CRB_N_PIPE; ++s) CRB_CUDA(cudaStreamSynchronize(ctx->pipe_stream[s]));
+  return CRB_OK;
+}

@@ -1,0 +1,818 @@
+// crb_mpc.cu — batched bicycle-model MPC solve for sm_100a.
+//
+// Replaces mpc_solve() + FG_EVAL of the reference, src/model_predictive_control.cpp:188-346 (the
+// CppAD + IPOPT solve of the speed-and-steering NLP), for n independent agents per launch, plus the
+// plant step update() :69-81 and the reference-trajectory lookup calc_ref_trajectory() :130-170 /
+// calc_nearest_index() :107-127.
+//
+// Algorithm (BASELINE.json north_star: "horizon-T linearised dynamics, QP cost, Riccati factorise-
+// and-solve replacing IPOPT"): box-constrained DDP on the reference NLP.  Each outer iteration
+// linearises the dynamics :242-245 along the current roll-out (with their exact second derivatives),
+// runs a Riccati recursion on the (state, previous input) augmented system so that the input-rate
+// cost :207-210 is handled exactly, solves the 2-D box QP of every stage in closed form (|delta|,
+// |a| and the speed limits :288-301 folded into a bound on a_t), and rolls the clamped non-linear
+// dynamics forward with step halving until the cost decreases.  The executable specification is
+// oracle/crb_oracle_mpc.c; this kernel reproduces it BIT FOR BIT (explicit fmaf, -fmad=false,
+// polynomial sin/cos, IEEE divide/sqrt), so status words and iteration counts match exactly.
+//
+// Mapping: ONE THREAD PER PROBLEM.  The matrices are 4x4 / 2x4 / 2x2 with five non-trivial entries
+// in A and two in B: a warp per problem would idle >80 % of its lanes and pay shuffles for every
+// product, whereas a thread per problem keeps the whole stage in registers, runs pure FFMA with
+// ample ILP, and makes every global access a coalesced 128-byte line because all per-problem data
+// (trajectories, gains) live in SoA scratch arrays indexed [item][problem].  At the BASELINE size
+// (65 536 agents, 128 threads per CTA, <= 128 registers) the whole batch is resident in one wave.
+#include <math.h>
+
+#include "crb_common.cuh"
+
+struct MpcP {
+  float dt, inv_dt, inv_wb, max_steer, max_accel, max_speed, min_speed;
+  float w_a, w_delta, w_da, w_ddelta;
+  float wq[4];
+  int max_iter;
+  float du_th;
+  int max_ls;
+};
+
+#define REG_EPS 1.0e-3f
+#define NGAIN 14  // k[2], Kx[2][4], Kw[2][2]
+
+// sin/cos: Cody-Waite reduction by pi/2 + minimax polynomials (same operations as the oracle's
+// crb_oracle_sincosf; libm / CUDA sinf are NOT used so that CPU and GPU agree to the bit).
+__device__ __forceinline__ void crb_sincosf(float x, float& sn, float& cs) {
+  if (!(fabsf(x) <= 1.0e5f)) {
+    sn = x - x;
+    cs = x - x;
+    if (fabsf(x) > 1.0e5f && x - x == 0.0f) {
+      sn = 0.0f;
+      cs = 1.0f;
+    }
+    return;
+  }
+  const float j = rintf(x * 0.63661977236758134308f);
+  float r = fmaf(-j, 1.5707962512969970703125f, x);
+  r = fmaf(-j, 7.5497894158615963533521e-08f, r);
+  r = fmaf(-j, 5.3903029534742383e-15f, r);
+  const int q = (int)j & 3;
+  const float z = r * r;
+  float ps = fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f);
+  ps = fmaf(ps, z, -1.6666654611e-1f);
+  ps = ps * z;
+  ps = fmaf(ps, r, r);
+  float pc = fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f);
+  pc = fmaf(pc, z, 4.166664568298827e-2f);
+  pc = pc * z;
+  pc = fmaf(pc, z, fmaf(-0.5f, z, 1.0f));
+  float s_ = (q & 1) ? pc : ps;
+  float c_ = (q & 1) ? ps : pc;
+  if (q & 2) s_ = -s_;
+  if ((q + 1) & 2) c_ = -c_;
+  sn = s_;
+  cs = c_;
+}
+
+__device__ __forceinline__ void a_bounds(float v, const MpcP& p, float& lo, float& hi, bool& lo_sp,
+                                         bool& hi_sp) {
+  const float lo_v = (p.min_speed - v) * p.inv_dt;
+  const float hi_v = (p.max_speed - v) * p.inv_dt;
+  const float am = p.max_accel;
+  float l = lo_v < am ? lo_v : am;
+  l = l > -am ? l : -am;
+  float h = hi_v > -am ? hi_v : -am;
+  h = h < am ? h : am;
+  lo = l;
+  hi = h;
+  lo_sp = lo_v > -am;
+  hi_sp = hi_v < am;
+}
+
+__device__ __forceinline__ float clampf(float u, float lo, float hi) {
+  return u < lo ? lo : (u > hi ? hi : u);
+}
+
+// x_{t+1} = f(x_t, u_t), src/model_predictive_control.cpp:242-245
+__device__ __forceinline__ void dyn_step(const float (&x)[4], float delta, float a, const MpcP& p,
+                                         float (&xn)[4]) {
+  float s, c, sd, cd;
+  crb_sincosf(x[2], s, c);
+  crb_sincosf(delta, sd, cd);
+  const float kap = (sd / cd) * p.inv_wb;
+  const float vdt = x[3] * p.dt;
+  xn[0] = fmaf(vdt, c, x[0]);
+  xn[1] = fmaf(vdt, s, x[1]);
+  xn[2] = fmaf(vdt, kap, x[2]);
+  xn[3] = fmaf(a, p.dt, x[3]);
+}
+
+// Exact minimiser of 0.5 u'Hu + g'u over a 2-D box (see box_qp2 in the oracle).
+__device__ __forceinline__ void box_qp2(float H00, float H01, float H11, float g0, float g1,
+                                        float lo0, float lo1, float hi0, float hi1, float idet,
+                                        float ih00, float ih11, float& k0, float& k1, bool& cl0,
+                                        bool& cl1) {
+  const float n0 = fmaf(H01, g1, -(H11 * g0));
+  const float n1 = fmaf(H01, g0, -(H00 * g1));
+  const float u0 = n0 * idet, u1 = n1 * idet;
+  if (u0 >= lo0 && u0 <= hi0 && u1 >= lo1 && u1 <= hi1) {
+    k0 = u0; k1 = u1; cl0 = false; cl1 = false;
+    return;
+  }
+  float best = INFINITY;
+  k0 = lo0 > 0.0f ? lo0 : (hi0 < 0.0f ? hi0 : 0.0f);
+  k1 = lo1 > 0.0f ? lo1 : (hi1 < 0.0f ? hi1 : 0.0f);
+  cl0 = true; cl1 = true;
+  // edges with u0 fixed (i = 0, j = 1), then u1 fixed (i = 1, j = 0); lo side before hi side
+#pragma unroll
+  for (int side = 0; side < 2; ++side) {
+    const float b = side ? hi0 : lo0;
+    float uj = -(fmaf(H01, b, g1) * ih11);
+    bool cj = false;
+    if (uj <= lo1) { uj = lo1; cj = true; }
+    else if (uj >= hi1) { uj = hi1; cj = true; }
+    const float ti = fmaf(0.5f * H00, b, g0);
+    const float tj = fmaf(0.5f * H11, uj, g1);
+    const float val = fmaf(ti, b, fmaf(tj, uj, (H01 * b) * uj));
+    if (val < best) { best = val; k0 = b; k1 = uj; cl0 = true; cl1 = cj; }
+  }
+#pragma unroll
+  for (int side = 0; side < 2; ++side) {
+    const float b = side ? hi1 : lo1;
+    float uj = -(fmaf(H01, b, g0) * ih00);
+    bool cj = false;
+    if (uj <= lo0) { uj = lo0; cj = true; }
+    else if (uj >= hi0) { uj = hi0; cj = true; }
+    const float ti = fmaf(0.5f * H11, b, g1);
+    const float tj = fmaf(0.5f * H00, uj, g0);
+    const float val = fmaf(ti, b, fmaf(tj, uj, (H01 * b) * uj));
+    if (val < best) { best = val; k1 = b; k0 = uj; cl1 = true; cl0 = cj; }
+  }
+}
+
+// ---- backward sweep -------------------------------------------------------------------------------
+// X [4T][n], U [2(T-1)][n] (field 2t+c, c = 0 delta, 1 a), xref [4T][n] (course frame; ox, oy are
+// subtracted on the fly), gains out G [14(T-1)][n].
+__device__ __forceinline__ void backward_sweep(int T, int64_t n, int64_t i, const float* X,
+                                               const float* U, const float* xref, float ox,
+                                               float oy, const MpcP& p, float* G) {
+  const int N = T - 1;
+  const float R2[2] = {2.0f * p.w_delta, 2.0f * p.w_a};
+  const float Rd2[2] = {2.0f * p.w_ddelta, 2.0f * p.w_da};
+  const float Q2[4] = {2.0f * p.wq[0], 2.0f * p.wq[1], 2.0f * p.wq[2], 2.0f * p.wq[3]};
+  const float dt = p.dt;
+  float Pxx[4][4], Pxw[4][2], Pww[2][2], px[4], pw[2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+#pragma unroll
+    for (int b = 0; b < 4; ++b) Pxx[a][b] = a == b ? Q2[a] : 0.0f;
+    Pxw[a][0] = 0.0f; Pxw[a][1] = 0.0f;
+  }
+  Pww[0][0] = Pww[0][1] = Pww[1][0] = Pww[1][1] = 0.0f;
+  pw[0] = pw[1] = 0.0f;
+  {
+    const float off[4] = {ox, oy, 0.0f, 0.0f};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float xr = k < 2 ? xref[((int64_t)N * 4 + k) * n + i] - off[k]
+                             : xref[((int64_t)N * 4 + k) * n + i];
+      px[k] = Q2[k] * (X[((int64_t)N * 4 + k) * n + i] - xr);
+    }
+  }
+  float ut[2];  // U[t]
+  ut[0] = U[((int64_t)(N - 1) * 2 + 0) * n + i];
+  ut[1] = U[((int64_t)(N - 1) * 2 + 1) * n + i];
+
+  for (int t = N - 1; t >= 0; --t) {
+    const bool hr = t >= 1;
+    float xt[4], xr[4], um[2] = {0.0f, 0.0f};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) xt[k] = X[((int64_t)t * 4 + k) * n + i];
+    if (hr) {
+      xr[0] = xref[((int64_t)t * 4 + 0) * n + i] - ox;
+      xr[1] = xref[((int64_t)t * 4 + 1) * n + i] - oy;
+      xr[2] = xref[((int64_t)t * 4 + 2) * n + i];
+      xr[3] = xref[((int64_t)t * 4 + 3) * n + i];
+      um[0] = U[((int64_t)(t - 1) * 2 + 0) * n + i];
+      um[1] = U[((int64_t)(t - 1) * 2 + 1) * n + i];
+    } else {
+      xr[0] = xr[1] = xr[2] = xr[3] = 0.0f;
+    }
+    const float v = xt[3];
+    float s, c, sd, cd;
+    crb_sincosf(xt[2], s, c);
+    crb_sincosf(ut[0], sd, cd);
+    const float tn = sd / cd;
+    const float kap = tn * p.inv_wb;
+    const float vdt = v * dt;
+    const float bv = (dt * p.inv_wb) * fmaf(tn, tn, 1.0f);
+    const float B20 = v * bv;
+    // A = I + {(0,2) a02, (0,3) a03, (1,2) a12, (1,3) a13, (2,3) a23};  B = {(2,0) B20, (3,1) dt}
+    const float a02 = -(vdt * s), a03 = c * dt, a12 = vdt * c, a13 = s * dt, a23 = kap * dt;
+
+    // gradients: qx = A^T px (+ Q2 (x - r)), qu = R2 u (+ Rd2 du) + B^T px + pw, qw = -Rd2 du
+    float qx[4], qu[2], qw[2], du[2] = {0.0f, 0.0f};
+    qx[0] = px[0];
+    qx[1] = px[1];
+    qx[2] = px[2] + fmaf(a12, px[1], a02 * px[0]);
+    qx[3] = px[3] + fmaf(a23, px[2], fmaf(a13, px[1], a03 * px[0]));
+    if (hr) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) qx[k] = fmaf(Q2[k], xt[k] - xr[k], qx[k]);
+    }
+    const float BtPx[2] = {B20 * px[2], dt * px[3]};
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      if (hr) du[a] = ut[a] - um[a];
+      float g = R2[a] * ut[a];
+      if (hr) g = fmaf(Rd2[a], du[a], g);
+      g = g + BtPx[a];
+      g = g + pw[a];
+      qu[a] = g;
+      qw[a] = hr ? -(Rd2[a] * du[a]) : 0.0f;
+    }
+    const float hyy = -(vdt * fmaf(px[1], s, px[0] * c));
+    const float hyv = dt * fmaf(px[1], c, -(px[0] * s));
+
+    // G = Pxx A (structural zeros/ones of A skipped; same term order as the dense product)
+    float Gm[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      Gm[a][0] = Pxx[a][0];
+      Gm[a][1] = Pxx[a][1];
+      Gm[a][2] = Pxx[a][2] + fmaf(Pxx[a][1], a12, Pxx[a][0] * a02);
+      Gm[a][3] = Pxx[a][3] + fmaf(Pxx[a][2], a23, fmaf(Pxx[a][1], a13, Pxx[a][0] * a03));
+    }
+    // Qxx = A^T G (+ Q2) (+ second-order terms), lower triangle only
+    float Qxx[4][4];
+    Qxx[0][0] = Gm[0][0];
+    Qxx[1][0] = Gm[1][0];
+    Qxx[1][1] = Gm[1][1];
+#pragma unroll
+    for (int b = 0; b < 3; ++b) Qxx[2][b] = Gm[2][b] + fmaf(a12, Gm[1][b], a02 * Gm[0][b]);
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      Qxx[3][b] = Gm[3][b] + fmaf(a23, Gm[2][b], fmaf(a13, Gm[1][b], a03 * Gm[0][b]));
+    if (hr) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) Qxx[a][a] = Qxx[a][a] + Q2[a];
+    }
+    Qxx[2][2] = Qxx[2][2] + hyy;
+    Qxx[3][2] = Qxx[3][2] + hyv;
+    // Qux = B^T G + Pwx A (+ second-order)
+    float Qux[2][4];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const float w0 = Pxw[0][a], w1 = Pxw[1][a], w2 = Pxw[2][a], w3 = Pxw[3][a];
+      const float W0 = w0, W1 = w1;
+      const float W2 = w2 + fmaf(w1, a12, w0 * a02);
+      const float W3 = w3 + fmaf(w2, a23, fmaf(w1, a13, w0 * a03));
+      const float bb = a == 0 ? B20 : dt;
+      const int row = a == 0 ? 2 : 3;
+      Qux[a][0] = bb * Gm[row][0] + W0;
+      Qux[a][1] = bb * Gm[row][1] + W1;
+      Qux[a][2] = bb * Gm[row][2] + W2;
+      Qux[a][3] = bb * Gm[row][3] + W3;
+    }
+    Qux[0][3] = fmaf(px[2], bv, Qux[0][3]);
+    // Quu = Luu + B^T Pxx B + B^T Pxw + Pwx B + Pww (+ second-order)
+    const float PB20 = Pxx[2][2] * B20, PB21 = Pxx[2][3] * dt, PB31 = Pxx[3][3] * dt;
+    const float BtPB00 = B20 * PB20, BtPB01 = B20 * PB21, BtPB11 = dt * PB31;
+    const float BtPxw00 = B20 * Pxw[2][0], BtPxw01 = B20 * Pxw[2][1];
+    const float BtPxw10 = dt * Pxw[3][0], BtPxw11 = dt * Pxw[3][1];
+    const float L0 = hr ? R2[0] + Rd2[0] : R2[0];
+    const float L1 = hr ? R2[1] + Rd2[1] : R2[1];
+    float Q00 = (((L0 + BtPB00) + BtPxw00) + BtPxw00) + Pww[0][0];
+    const float Q01 = (((0.0f + BtPB01) + BtPxw01) + BtPxw10) + Pww[0][1];
+    const float Q11 = (((L1 + BtPB11) + BtPxw11) + BtPxw11) + Pww[1][1];
+    Q00 = fmaf(px[2], (2.0f * tn) * B20, Q00);
+    const float Quw[2] = {hr ? -Rd2[0] : 0.0f, hr ? -Rd2[1] : 0.0f};
+    const float Qww[2] = {hr ? Rd2[0] : 0.0f, hr ? Rd2[1] : 0.0f};
+
+    // positive-definite shift for the gains
+    const float mh = 0.5f * (Q00 + Q11), dh = 0.5f * (Q00 - Q11);
+    const float lam = mh - sqrtf(fmaf(dh, dh, Q01 * Q01));
+    const float shift = lam < REG_EPS ? REG_EPS - lam : 0.0f;
+    const float H00 = Q00 + shift, H11 = Q11 + shift, H01 = Q01;
+    const float det = fmaf(H00, H11, -(H01 * H01));
+    const float idet = 1.0f / det, ih00 = 1.0f / H00, ih11 = 1.0f / H11;
+
+    float alo, ahi;
+    bool lo_sp, hi_sp;
+    a_bounds(v, p, alo, ahi, lo_sp, hi_sp);
+    const float lo0 = -p.max_steer - ut[0], lo1 = alo - ut[1];
+    const float hi0 = p.max_steer - ut[0], hi1 = ahi - ut[1];
+    float k0, k1;
+    bool cl0, cl1;
+    box_qp2(H00, H01, H11, qu[0], qu[1], lo0, lo1, hi0, hi1, idet, ih00, ih11, k0, k1, cl0, cl1);
+    float Kx[2][4], Kw[2][2];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) { Kx[0][b] = 0.0f; Kx[1][b] = 0.0f; }
+    Kw[0][0] = Kw[0][1] = Kw[1][0] = Kw[1][1] = 0.0f;
+    if (cl1) {
+      const bool at_lo = k1 <= lo1;
+      if ((at_lo && lo_sp) || (!at_lo && hi_sp)) Kx[1][3] = -p.inv_dt;
+    }
+    if (!cl0 && !cl1) {
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        Kx[0][b] = fmaf(H01, Qux[1][b], -(H11 * Qux[0][b])) * idet;
+        Kx[1][b] = fmaf(H01, Qux[0][b], -(H00 * Qux[1][b])) * idet;
+      }
+      Kw[0][0] = fmaf(H01, 0.0f, -(H11 * Quw[0])) * idet;
+      Kw[1][0] = fmaf(H01, Quw[0], -(H00 * 0.0f)) * idet;
+      Kw[0][1] = fmaf(H01, Quw[1], -(H11 * 0.0f)) * idet;
+      Kw[1][1] = fmaf(H01, 0.0f, -(H00 * Quw[1])) * idet;
+    } else if (!cl0) {  // delta free (j = 0), a clamped (i = 1)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) Kx[0][b] = -(fmaf(H01, Kx[1][b], Qux[0][b]) * ih00);
+      Kw[0][0] = -(fmaf(H01, Kw[1][0], Quw[0]) * ih00);
+      Kw[0][1] = -(fmaf(H01, Kw[1][1], 0.0f) * ih00);
+    } else if (!cl1) {  // a free (j = 1), delta clamped (i = 0)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) Kx[1][b] = -(fmaf(H01, Kx[0][b], Qux[1][b]) * ih11);
+      Kw[1][0] = -(fmaf(H01, Kw[0][0], 0.0f) * ih11);
+      Kw[1][1] = -(fmaf(H01, Kw[0][1], Quw[1]) * ih11);
+    }
+    // store gains for the forward sweeps
+    {
+      float* g = G + ((int64_t)t * NGAIN) * n + i;
+      g[0 * n] = k0; g[1 * n] = k1;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) { g[(2 + b) * n] = Kx[0][b]; g[(6 + b) * n] = Kx[1][b]; }
+      g[10 * n] = Kw[0][0]; g[11 * n] = Kw[0][1]; g[12 * n] = Kw[1][0]; g[13 * n] = Kw[1][1];
+    }
+    // value-function update for du = k + Kx dx + Kw dw with the TRUE Quu
+    const float m0 = fmaf(Q01, k1, fmaf(Q00, k0, qu[0]));
+    const float m1 = fmaf(Q11, k1, fmaf(Q01, k0, qu[1]));
+    float Mx[2][4], Mw[2][2];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      Mx[0][b] = fmaf(Q01, Kx[1][b], fmaf(Q00, Kx[0][b], Qux[0][b]));
+      Mx[1][b] = fmaf(Q11, Kx[1][b], fmaf(Q01, Kx[0][b], Qux[1][b]));
+    }
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      Mw[0][b] = fmaf(Q01, Kw[1][b], fmaf(Q00, Kw[0][b], b == 0 ? Quw[0] : 0.0f));
+      Mw[1][b] = fmaf(Q11, Kw[1][b], fmaf(Q01, Kw[0][b], b == 1 ? Quw[1] : 0.0f));
+    }
+    float npx[4], npw[2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      float acc = qx[a];
+      acc = fmaf(Kx[0][a], m0, acc);
+      acc = fmaf(Kx[1][a], m1, acc);
+      acc = fmaf(Qux[0][a], k0, acc);
+      acc = fmaf(Qux[1][a], k1, acc);
+      npx[a] = acc;
+    }
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      float acc = qw[b];
+      acc = fmaf(Kw[0][b], m0, acc);
+      acc = fmaf(Kw[1][b], m1, acc);
+      acc = fmaf(Quw[b], b == 0 ? k0 : k1, acc);
+      npw[b] = acc;
+    }
+    float nPxx[4][4], nPxw[4][2], nPww[2][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+#pragma unroll
+      for (int b = 0; b <= a; ++b) {
+        float acc = Qxx[a][b];
+        acc = fmaf(Kx[0][a], Mx[0][b], acc);
+        acc = fmaf(Kx[1][a], Mx[1][b], acc);
+        acc = fmaf(Qux[0][a], Kx[0][b], acc);
+        acc = fmaf(Qux[1][a], Kx[1][b], acc);
+        nPxx[a][b] = acc;
+        nPxx[b][a] = acc;
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        float acc = Kx[0][a] * Mw[0][b];
+        acc = fmaf(Kx[1][a], Mw[1][b], acc);
+        acc = fmaf(Qux[0][a], Kw[0][b], acc);
+        acc = fmaf(Qux[1][a], Kw[1][b], acc);
+        nPxw[a][b] = acc;
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+#pragma unroll
+      for (int b = 0; b <= a; ++b) {
+        float acc = a == b ? Qww[a] : 0.0f;
+        acc = fmaf(Kw[0][a], Mw[0][b], acc);
+        acc = fmaf(Kw[1][a], Mw[1][b], acc);
+        acc = fmaf(Quw[a], Kw[a][b], acc);
+        nPww[a][b] = acc;
+        nPww[b][a] = acc;
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+#pragma unroll
+      for (int b = 0; b < 4; ++b) Pxx[a][b] = nPxx[a][b];
+      Pxw[a][0] = nPxw[a][0]; Pxw[a][1] = nPxw[a][1];
+      px[a] = npx[a];
+    }
+    Pww[0][0] = nPww[0][0]; Pww[0][1] = nPww[0][1]; Pww[1][0] = nPww[1][0]; Pww[1][1] = nPww[1][1];
+    pw[0] = npw[0]; pw[1] = npw[1];
+    ut[0] = um[0]; ut[1] = um[1];
+  }
+}
+
+// ---- forward sweep: clamped roll-out under the affine policy; returns dJ and sum|du| ----------------
+__device__ __forceinline__ void forward_sweep(int T, int64_t n, int64_t i, float yaw0, float v0,
+                                              const float* X, const float* U, const float* xref,
+                                              float ox, float oy, const float* G, float alpha,
+                                              const MpcP& p, float* Xn, float* Un, float& dJ_out,
+                                              float& du_out) {
+  float dJ = 0.0f, dus = 0.0f;
+  float xn[4] = {0.0f, 0.0f, yaw0, v0};   // Xn[t]
+  float xo[4] = {0.0f, 0.0f, yaw0, v0};   // X[t]  (both roll-outs start at x0)
+  float unm[2] = {0.0f, 0.0f}, uom[2] = {0.0f, 0.0f};  // Un[t-1], U[t-1]
+#pragma unroll
+  for (int k = 0; k < 4; ++k) Xn[(int64_t)k * n + i] = xn[k];
+  const float wu[2] = {p.w_delta, p.w_a};
+  const float wd[2] = {p.w_ddelta, p.w_da};
+  for (int t = 0; t < T - 1; ++t) {
+    const float* g = G + ((int64_t)t * NGAIN) * n + i;
+    float uo[2];
+    uo[0] = U[((int64_t)t * 2 + 0) * n + i];
+    uo[1] = U[((int64_t)t * 2 + 1) * n + i];
+    float gk[NGAIN];
+#pragma unroll
+    for (int j = 0; j < NGAIN; ++j) gk[j] = g[(int64_t)j * n];
+    float xo1[4], xr1[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) xo1[k] = X[((int64_t)(t + 1) * 4 + k) * n + i];
+    xr1[0] = xref[((int64_t)(t + 1) * 4 + 0) * n + i] - ox;
+    xr1[1] = xref[((int64_t)(t + 1) * 4 + 1) * n + i] - oy;
+    xr1[2] = xref[((int64_t)(t + 1) * 4 + 2) * n + i];
+    xr1[3] = xref[((int64_t)(t + 1) * 4 + 3) * n + i];
+    float dx[4], dw[2] = {0.0f, 0.0f};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dx[k] = xn[k] - xo[k];
+    if (t >= 1) { dw[0] = unm[0] - uom[0]; dw[1] = unm[1] - uom[1]; }
+    float u[2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      float acc = fmaf(alpha, gk[a], uo[a]);
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc = fmaf(gk[2 + 4 * a + b], dx[b], acc);
+#pragma unroll
+      for (int b = 0; b < 2; ++b) acc = fmaf(gk[10 + 2 * a + b], dw[b], acc);
+      u[a] = acc;
+    }
+    u[0] = clampf(u[0], -p.max_steer, p.max_steer);
+    float alo, ahi;
+    bool s0, s1;
+    a_bounds(xn[3], p, alo, ahi, s0, s1);
+    u[1] = clampf(u[1], alo, ahi);
+    Un[((int64_t)t * 2 + 0) * n + i] = u[0];
+    Un[((int64_t)t * 2 + 1) * n + i] = u[1];
+    float xn1[4];
+    dyn_step(xn, u[0], u[1], p, xn1);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) Xn[((int64_t)(t + 1) * 4 + k) * n + i] = xn1[k];
+    // cost difference, term by term: w (q' - q)(q' + q)
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const float d = u[a] - uo[a], sm = u[a] + uo[a];
+      dJ = fmaf(wu[a] * d, sm, dJ);
+      dus = dus + fabsf(d);
+    }
+    if (t >= 1) {
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        const float qn = u[a] - unm[a], qo = uo[a] - uom[a];
+        dJ = fmaf(wd[a] * (qn - qo), qn + qo, dJ);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float en = xn1[k] - xr1[k], eo = xo1[k] - xr1[k];
+      dJ = fmaf(p.wq[k] * (xn1[k] - xo1[k]), en + eo, dJ);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { xn[k] = xn1[k]; xo[k] = xo1[k]; }
+    unm[0] = u[0]; unm[1] = u[1]; uom[0] = uo[0]; uom[1] = uo[1];
+  }
+  dJ_out = dJ;
+  du_out = dus;
+}
+
+// fg[0] (:199-250) on a stored roll-out, same term order as direct_cost() in the oracle
+__device__ __forceinline__ float direct_cost(int T, int64_t n, int64_t i, const float* X,
+                                             const float* U, const float* xref, float ox, float oy,
+                                             const MpcP& p) {
+  float J = 0.0f;
+  float um[2] = {0.0f, 0.0f};
+  for (int t = 0; t < T - 1; ++t) {
+    const float d = U[((int64_t)t * 2 + 0) * n + i], a = U[((int64_t)t * 2 + 1) * n + i];
+    J = fmaf(p.w_delta * d, d, J);
+    J = fmaf(p.w_a * a, a, J);
+    if (t >= 1) {
+      const float dd = d - um[0], da = a - um[1];
+      J = fmaf(p.w_ddelta * dd, dd, J);
+      J = fmaf(p.w_da * da, da, J);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float xr = xref[((int64_t)(t + 1) * 4 + k) * n + i];
+      if (k == 0) xr = xr - ox;
+      if (k == 1) xr = xr - oy;
+      const float e = X[((int64_t)(t + 1) * 4 + k) * n + i] - xr;
+      J = fmaf(p.wq[k] * e, e, J);
+    }
+    um[0] = d; um[1] = a;
+  }
+  return J;
+}
+
+__global__ void __launch_bounds__(128)
+crb_mpc_solve_kernel(int64_t count, int64_t ld_in, int T, const float* __restrict__ x0,
+                     const float* __restrict__ xref, const float* __restrict__ u_init,
+                     float* __restrict__ XA, float* __restrict__ XB, float* __restrict__ UA,
+                     float* __restrict__ UB, float* __restrict__ G, int64_t ld_out,
+                     float* __restrict__ sol, float* __restrict__ u0, float* __restrict__ cost,
+                     int32_t* __restrict__ status, int32_t* __restrict__ iters, const MpcP p) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int64_t n = ld_in;  // scratch and inputs share the leading dimension
+  const int N = T - 1;
+  const float ox = x0[0 * n + i], oy = x0[1 * n + i];
+  const float yaw0 = x0[2 * n + i], v0 = x0[3 * n + i];
+  float* X = XA; float* Xn = XB; float* U = UA; float* Un = UB;
+  // initial clamped roll-out (cold start: zeros, :266-269) in the frame translated to (ox, oy)
+  {
+    float x[4] = {0.0f, 0.0f, yaw0, v0};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) X[(int64_t)k * n + i] = x[k];
+    for (int t = 0; t < N; ++t) {
+      float d = u_init ? u_init[(int64_t)t * n + i] : 0.0f;
+      float a = u_init ? u_init[(int64_t)(N + t) * n + i] : 0.0f;
+      d = clampf(d, -p.max_steer, p.max_steer);
+      float alo, ahi;
+      bool s0, s1;
+      a_bounds(x[3], p, alo, ahi, s0, s1);
+      a = clampf(a, alo, ahi);
+      U[((int64_t)t * 2 + 0) * n + i] = d;
+      U[((int64_t)t * 2 + 1) * n + i] = a;
+      float x1[4];
+      dyn_step(x, d, a, p, x1);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { x[k] = x1[k]; X[((int64_t)(t + 1) * 4 + k) * n + i] = x1[k]; }
+    }
+  }
+  int st = CRB_MPC_MAX_ITER, it_count = 0;
+  const float J0 = direct_cost(T, n, i, X, U, xref, ox, oy, p);
+  if (!(fabsf(J0) <= 3.0e38f)) {
+    st = CRB_MPC_NONFINITE;
+  } else {
+    for (int it = 0; it < p.max_iter; ++it) {
+      backward_sweep(T, n, i, X, U, xref, ox, oy, p, G);
+      ++it_count;
+      bool accepted = false;
+      float dJ = 0.0f, du = 0.0f, alpha = 1.0f;
+      for (int j = 0; j <= p.max_ls; ++j) {
+        forward_sweep(T, n, i, yaw0, v0, X, U, xref, ox, oy, G, alpha, p, Xn, Un, dJ, du);
+        if (dJ < 0.0f) { accepted = true; break; }
+        alpha = alpha * 0.5f;
+      }
+      if (!accepted) { st = CRB_MPC_NO_DESCENT; break; }
+      float* tx = X; X = Xn; Xn = tx;
+      float* tu = U; U = Un; Un = tu;
+      if (du <= p.du_th) { st = CRB_MPC_CONVERGED; break; }
+    }
+  }
+  const float J = direct_cost(T, n, i, X, U, xref, ox, oy, p);
+  if (!(fabsf(J) <= 3.0e38f)) st = CRB_MPC_NONFINITE;
+  const int64_t m = ld_out;
+  if (sol) {  // the reference's return layout, :54-60
+    for (int t = 0; t < T; ++t) {
+      sol[((int64_t)0 * T + t) * m + i] = X[((int64_t)t * 4 + 0) * n + i] + ox;
+      sol[((int64_t)1 * T + t) * m + i] = X[((int64_t)t * 4 + 1) * n + i] + oy;
+      sol[((int64_t)2 * T + t) * m + i] = X[((int64_t)t * 4 + 2) * n + i];
+      sol[((int64_t)3 * T + t) * m + i] = X[((int64_t)t * 4 + 3) * n + i];
+    }
+    for (int t = 0; t < N; ++t) {
+      sol[((int64_t)4 * T + t) * m + i] = U[((int64_t)t * 2 + 0) * n + i];
+      sol[((int64_t)4 * T + N + t) * m + i] = U[((int64_t)t * 2 + 1) * n + i];
+    }
+  }
+  if (u0) {  // (a_0, delta_0): what the caller feeds update(), :376
+    u0[0 * m + i] = U[(int64_t)1 * n + i];
+    u0[1 * m + i] = U[(int64_t)0 * n + i];
+  }
+  if (cost) cost[i] = J;
+  if (status) status[i] = st;
+  if (iters) iters[i] = it_count;
+}
+
+static void mpc_fill(MpcP* p, const crb_mpc_params* prm) {
+  p->dt = prm->dt;
+  p->inv_dt = 1.0f / prm->dt;
+  p->inv_wb = 1.0f / prm->wb;
+  p->max_steer = prm->max_steer;
+  p->max_accel = prm->max_accel;
+  p->max_speed = prm->max_speed;
+  p->min_speed = prm->min_speed;
+  p->w_a = prm->w_a; p->w_delta = prm->w_delta; p->w_da = prm->w_da; p->w_ddelta = prm->w_ddelta;
+  p->wq[0] = prm->w_x; p->wq[1] = prm->w_y; p->wq[2] = prm->w_yaw; p->wq[3] = prm->w_v;
+  p->max_iter = prm->max_iter;
+  p->du_th = prm->du_th;
+  p->max_ls = prm->max_ls;
+}
+
+static size_t mpc_scratch_floats(int T) { return (size_t)8 * T + (size_t)(4 + NGAIN) * (T - 1); }
+
+// inputs x0/xref/u_init and the scratch arrays all have leading dimension ld (>= count)
+static int mpc_launch(crb_ctx* ctx, cudaStream_t st, int64_t count, int64_t ld, int T,
+                      const float* x0, const float* xref, const float* u_init, float* scratch,
+                      int64_t ld_out, float* sol, float* u0, float* cost, int32_t* status,
+                      int32_t* iters, const crb_mpc_params* prm) {
+  MpcP p;
+  mpc_fill(&p, prm);
+  float* XA = scratch;
+  float* XB = XA + (size_t)4 * T * ld;
+  float* UA = XB + (size_t)4 * T * ld;
+  float* UB = UA + (size_t)2 * (T - 1) * ld;
+  float* G = UB + (size_t)2 * (T - 1) * ld;
+  const int block = 128;
+  crb_mpc_solve_kernel<<<crb_grid_for(count, block), block, 0, st>>>(
+      count, ld, T, x0, xref, u_init, XA, XB, UA, UB, G, ld_out, sol, u0, cost, status, iters, p);
+  CRB_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return CRB_OK;
+}
+
+static int mpc_check(crb_ctx* ctx, int64_t n, int T, const float* x0, const float* xref,
+                     const crb_mpc_params* prm) {
+  CRB_REQUIRE(ctx != nullptr, "ctx is NULL");
+  CRB_REQUIRE(prm != nullptr, "prm is NULL");
+  CRB_REQUIRE(n >= 0, "n < 0");
+  CRB_REQUIRE(T >= 2 && T <= CRB_MPC_MAX_T, "T out of range [2, CRB_MPC_MAX_T]");
+  CRB_REQUIRE(prm->dt > 0.0f && prm->wb > 0.0f, "dt and wb must be positive");
+  CRB_REQUIRE(prm->max_iter >= 0 && prm->max_ls >= 0, "max_iter / max_ls negative");
+  CRB_REQUIRE(n == 0 || (x0 && xref), "NULL array");
+  return CRB_OK;
+}
+
+extern "C" int crb_mpc_solve_batched(crb_ctx* ctx, int64_t n, int T, const float* x0,
+                                     const float* xref, const float* u_init,
+                                     const crb_mpc_params* prm, float* sol, float* u0, float* cost,
+                                     int32_t* status, int32_t* iters) {
+  int rc = mpc_check(ctx, n, T, x0, xref, prm);
+  if (rc) return rc;
+  if (n == 0) return CRB_OK;
+  rc = crb_ctx_mpc_ws_reserve(ctx, mpc_scratch_floats(T) * (size_t)n * sizeof(float));
+  if (rc) return rc;
+  return mpc_launch(ctx, ctx->stream, n, n, T, x0, xref, u_init, (float*)ctx->mpc_ws, n, sol,
+                    u0, cost, status, iters, prm);
+}
+
+extern "C" int crb_mpc_solve_batched_host(crb_ctx* ctx, int64_t n, int T, const float* x0,
+                                          const float* xref, const float* u_init,
+                                          const crb_mpc_params* prm, float* sol, float* u0,
+                                          float* cost, int32_t* status, int32_t* iters) {
+  int rc = mpc_check(ctx, n, T, x0, xref, prm);
+  if (rc) return rc;
+  if (n == 0) return CRB_OK;
+  CRB_CUDA(cudaSetDevice(ctx->device));
+  const int N = T - 1;
+  const int64_t chunk_cap = n < (int64_t)32768 ? n : (int64_t)32768;
+  const size_t nsol = (size_t)4 * T + 2 * N;
+  // per slot: inputs (4 + 4T + 2N), outputs (nsol + 2 + 1 + 1 + 1), scratch
+  const size_t nf = (size_t)4 + 4 * T + 2 * N + nsol + 5 + mpc_scratch_floats(T);
+  const size_t pitch = (size_t)chunk_cap * sizeof(float);
+  for (int s = 0; s < CRB_N_PIPE; ++s) {
+    rc = crb_ctx_pipe_reserve(ctx, s, nf * pitch);
+    if (rc) return rc;
+  }
+  const size_t hp = (size_t)n * sizeof(float);
+  int slot = 0;
+  for (int64_t i0 = 0; i0 < n; i0 += chunk_cap, slot = (slot + 1) % CRB_N_PIPE) {
+    const int64_t cnt = (n - i0) < chunk_cap ? (n - i0) : chunk_cap;
+    cudaStream_t st = ctx->pipe_stream[slot];
+    float* dx0 = (float*)ctx->pipe_buf[slot];
+    float* dxr = dx0 + 4 * chunk_cap;
+    float* dui = dxr + (size_t)4 * T * chunk_cap;
+    float* dsol = dui + (size_t)2 * N * chunk_cap;
+    float* du0 = dsol + nsol * chunk_cap;
+    float* dcost = du0 + 2 * chunk_cap;
+    int32_t* dstat = (int32_t*)(dcost + chunk_cap);
+    int32_t* dit = dstat + chunk_cap;
+    float* scratch = (float*)(dit + chunk_cap);
+    const size_t w = (size_t)cnt * sizeof(float);
+    CRB_CUDA(cudaMemcpy2DAsync(dx0, pitch, x0 + i0, hp, w, 4, cudaMemcpyHostToDevice, st));
+    CRB_CUDA(cudaMemcpy2DAsync(dxr, pitch, xref + i0, hp, w, (size_t)4 * T, cudaMemcpyHostToDevice,
+                               st));
+    if (u_init)
+      CRB_CUDA(cudaMemcpy2DAsync(dui, pitch, u_init + i0, hp, w, (size_t)2 * N,
+                                 cudaMemcpyHostToDevice, st));
+    rc = mpc_launch(ctx, st, cnt, chunk_cap, T, dx0, dxr, u_init ? dui : nullptr, scratch,
+                    chunk_cap, sol ? dsol : nullptr, u0 ? du0 : nullptr, cost ? dcost : nullptr,
+                    status ? dstat : nullptr, iters ? dit : nullptr, prm);
+    if (rc) return rc;
+    if (sol)
+      CRB_CUDA(cudaMemcpy2DAsync(sol + i0, hp, dsol, pitch, w, nsol, cudaMemcpyDeviceToHost, st));
+    if (u0) CRB_CUDA(cudaMemcpy2DAsync(u0 + i0, hp, du0, pitch, w, 2, cudaMemcpyDeviceToHost, st));
+    if (cost) CRB_CUDA(cudaMemcpyAsync(cost + i0, dcost, w, cudaMemcpyDeviceToHost, st));
+    if (status) CRB_CUDA(cudaMemcpyAsync(status + i0, dstat, w, cudaMemcpyDeviceToHost, st));
+    if (iters) CRB_CUDA(cudaMemcpyAsync(iters + i0, dit, w, cudaMemcpyDeviceToHost, st));
+  }
+  for (int s = 0; s < CRB_N_PIPE; ++s) CRB_CUDA(cudaStreamSynchronize(ctx->pipe_stream[s]));
+  return CRB_OK;
+}
+
+// ---- update(): src/model_predictive_control.cpp:69-81 ------------------------------------------------
+// MAX_STEER, DT, WB, MAX_SPEED, MIN_SPEED are double macros in the reference, so the float operands
+// promote to double and the result narrows on assignment; cos/sin/tan are the float overloads.
+__global__ void __launch_bounds__(256)
+crb_mpc_plant_update_kernel(int64_t n, float* __restrict__ state, const float* __restrict__ u0) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double MAX_STEER = 45.0 / 180 * 3.14159265358979323846, DT = 0.2, WB = 2.5;
+  const double MAX_SPEED = 55.0 / 3.6, MIN_SPEED = -20.0 / 3.6;
+  const float a = u0[i];
+  float delta = u0[n + i];
+  if ((double)delta >= MAX_STEER) delta = (float)MAX_STEER;
+  if ((double)delta <= -MAX_STEER) delta = (float)(-MAX_STEER);
+  const float x = state[i], y = state[n + i], yaw = state[2 * n + i], v = state[3 * n + i];
+  const float nx = (float)((double)x + (double)(v * cosf(yaw)) * DT);
+  const float ny = (float)((double)y + (double)(v * sinf(yaw)) * DT);
+  const float nyaw = (float)((double)yaw + (double)v / WB * (double)tanf(delta) * DT);
+  float nv = (float)((double)v + (double)a * DT);
+  if ((double)nv > MAX_SPEED) nv = (float)MAX_SPEED;
+  if ((double)nv < MIN_SPEED) nv = (float)MIN_SPEED;
+  state[i] = nx; state[n + i] = ny; state[2 * n + i] = nyaw; state[3 * n + i] = nv;
+}
+
+extern "C" int crb_mpc_plant_update_batched(crb_ctx* ctx, int64_t n, float* state, const float* u0,
+                                            const crb_mpc_params* prm) {
+  CRB_REQUIRE(ctx != nullptr, "ctx is NULL");
+  CRB_REQUIRE(n >= 0, "n < 0");
+  (void)prm;  // update() uses the reference's compile-time macros, mirrored in the kernel
+  if (n == 0) return CRB_OK;
+  CRB_REQUIRE(state && u0, "NULL array");
+  crb_mpc_plant_update_kernel<<<crb_grid_for(n, 256), 256, 0, ctx->stream>>>(n, state, u0);
+  CRB_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return CRB_OK;
+}
+
+// ---- calc_ref_trajectory :130-170 with calc_nearest_index :107-127 -------------------------------------
+__global__ void __launch_bounds__(256)
+crb_mpc_ref_traj_kernel(int64_t n, int T, const float* __restrict__ state,
+                        const float* __restrict__ cx, const float* __restrict__ cy,
+                        const float* __restrict__ cyaw, const float* __restrict__ sp, int ncourse,
+                        float dl, int32_t* __restrict__ target_ind, float* __restrict__ xref) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float sx = state[i], sy = state[n + i], sv = state[3 * n + i];
+  const int pind = target_ind[i];
+  // calc_nearest_index: float-typed index (:109), strict '<' keeps the first minimum (:115)
+  float mind = 3.402823466e+38f;
+  float find = 0;
+  for (unsigned int j = (unsigned int)pind; j < (unsigned int)pind + 10u; ++j) {
+    if ((int)j >= ncourse) break;
+    const float idx = cx[j] - sx;
+    const float idy = cy[j] - sy;
+    const float d_e = idx * idx + idy * idy;
+    if (d_e < mind) { mind = d_e; find = (float)j; }
+  }
+  int ind = (int)find;
+  if (pind >= ind) ind = pind;  // :139
+  const double DT = 0.2;
+  float travel = 0.0f;
+  for (int t = 0; t < T; ++t) {
+    travel = (float)((double)travel + (double)fabsf(sv) * DT);  // :149
+    const int dind = (int)roundf(travel / dl);                  // :150
+    const int j = (ind + dind) < ncourse ? ind + dind : ncourse - 1;
+    xref[((int64_t)t * 4 + 0) * n + i] = cx[j];
+    xref[((int64_t)t * 4 + 1) * n + i] = cy[j];
+    xref[((int64_t)t * 4 + 2) * n + i] = cyaw[j];
+    xref[((int64_t)t * 4 + 3) * n + i] = sp[j];
+  }
+  target_ind[i] = ind;  // :169
+}
+
+extern "C" int crb_mpc_calc_ref_trajectory_batched(crb_ctx* ctx, int64_t n, int T,
+                                                   const float* state, const float* cx,
+                                                   const float* cy, const float* cyaw,
+                                                   const float* sp, int32_t ncourse, float dl,
+                                                   int32_t* target_ind, float* xref,
+                                                   const crb_mpc_params* prm) {
+  CRB_REQUIRE(ctx != nullptr, "ctx is NULL");
+  CRB_REQUIRE(n >= 0 && T >= 1 && T <= CRB_MPC_MAX_T, "n < 0 or T out of range");
+  CRB_REQUIRE(ncourse >= 1 && dl > 0.0f, "empty course or dl <= 0");
+  (void)prm;
+  if (n == 0) return CRB_OK;
+  CRB_REQUIRE(state && cx && cy && cyaw && sp && target_ind && xref, "NULL array");
+  crb_mpc_ref_traj_kernel<<<crb_grid_for(n, 256), 256, 0, ctx->stream>>>(
+      n, T, state, cx, cy, cyaw, sp, ncourse, dl, target_ind, xref);
+  CRB_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return CRB_OK;
+}

@@ -1,0 +1,215 @@
+/* crb.h — C ABI of the B200 batched small-matrix engine for the CppRobotics hot paths.
+ *
+ * The reference (onlytailei/CppRobotics) has no plugin / FFI surface: its hot functions are free
+ * functions inside executable translation units.  This header therefore *defines* the seam at the
+ * function signatures themselves; every entry point names the reference function it replaces.
+ *
+ *   crb_ekf_step_batched[_host]        <- ekf_estimation()      src/extended_kalman_filter.cpp:64-78
+ *                                         (motion_model :22-36, jacobF :38-47, observation_model :50-55,
+ *                                          jacobH :57-62 are folded into the same kernel)
+ *   crb_pf_predict_weight_batched[_host] <- pf_localization() particle loop  src/particle_filter.cpp:81-102
+ *                                         (motion_model :26-40, gauss_likelihood :53-57)
+ *   crb_pf_estimate                     <- pf_localization() tail            src/particle_filter.cpp:104-107
+ *                                         (calc_covariance :59-71)
+ *   crb_mpc_solve_batched[_host]        <- mpc_solve() + FG_EVAL            src/model_predictive_control.cpp:188-346
+ *   crb_mpc_plant_update_batched        <- update()                          src/model_predictive_control.cpp:69-81
+ *   crb_mpc_calc_ref_trajectory_batched <- calc_ref_trajectory() :130-170 + calc_nearest_index() :107-127
+ *   crb_stats_*                         <- (no reference counterpart) per-GPU summary statistics, the
+ *                                          only thing that ever crosses NVLink (one all-gather).
+ *
+ * Conventions
+ *   - Plain C, plain pointers and sizes.  No C++ / torch types.
+ *   - All batched arrays are SoA, "field-major": element (field f, agent i) lives at ptr[f*n + i].
+ *     Matrices are flattened column-major like Eigen fixed-size matrices: P(r,c) is field r + 4*c.
+ *   - Entry points without a suffix take DEVICE pointers and enqueue asynchronously on the context's
+ *     stream; `_host` variants take HOST pointers (pinned memory recommended, see crb_host_alloc),
+ *     stage through internal device buffers in chunks with copy/compute overlap, and return after
+ *     the results are in the caller's buffers.
+ *   - Return value: CRB_OK (0) or a negative crb_status.  crb_last_error_string() describes the last
+ *     failure on the calling thread.  The reference reports no errors at all (IPOPT status is dropped,
+ *     src/model_predictive_control.cpp:338-339); the per-agent MPC status word is additional.
+ *   - The caller owns every buffer.  A context is bound to one device and one stream and is not
+ *     thread-safe; use one context per host thread / per GPU (one process per GPU in this repo).
+ *   - There is NO CPU fallback: every compute entry point fails with CRB_ERR_NO_DEVICE when no CUDA
+ *     device is usable.
+ */
+#ifndef CRB_H_
+#define CRB_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRB_ABI_VERSION 1
+
+typedef enum crb_status {
+  CRB_OK = 0,
+  CRB_ERR_INVALID_ARG = -1,
+  CRB_ERR_NO_DEVICE = -2,
+  CRB_ERR_CUDA = -3,
+  CRB_ERR_ALLOC = -4,
+  CRB_ERR_UNSUPPORTED = -5
+} crb_status;
+
+typedef struct crb_ctx crb_ctx;
+
+/* ---- context ----------------------------------------------------------------------------- */
+int crb_abi_version(void);
+const char* crb_last_error_string(void);
+/* device_id < 0 -> current device.  Creates a private non-blocking stream. */
+int crb_init(crb_ctx** out, int device_id);
+int crb_destroy(crb_ctx* ctx);
+/* Use a caller-provided cudaStream_t (e.g. torch's current stream) instead of the private one;
+ * stream == NULL restores the private stream. */
+int crb_set_stream(crb_ctx* ctx, void* cuda_stream);
+void* crb_get_stream(crb_ctx* ctx);
+int crb_sync(crb_ctx* ctx);
+/* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
+int64_t crb_launch_count(crb_ctx* ctx);
+/* Pinned host memory helpers for the _host entry points. */
+int crb_host_alloc(void** out, size_t bytes);
+int crb_host_free(void* p);
+/* Device memory helpers (for callers that do not want to link the CUDA runtime themselves). */
+int crb_device_alloc(crb_ctx* ctx, void** out, size_t bytes);
+int crb_device_free(crb_ctx* ctx, void* p);
+int crb_memcpy_h2d(crb_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+int crb_memcpy_d2h(crb_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+/* Event timing on the context's stream (so that callers that only know the C ABI can time it). */
+int crb_timer_start(crb_ctx* ctx);
+int crb_timer_stop_ms(crb_ctx* ctx, float* ms_out); /* synchronises on the stop event */
+
+/* ---- EKF ------------------------------------------------------------------------------------ */
+/* Constants that live in main() of the reference: src/extended_kalman_filter.cpp:17 (DT),
+ * :142-146 (Q), :149-151 (R).  dt is a double because DT is a double literal in the reference and
+ * several entries are computed as (float)(DT * (double)cosf(yaw)).  Q, R column-major. */
+typedef struct crb_ekf_params {
+  double dt;
+  float Q[16];
+  float R[4];
+} crb_ekf_params;
+/* Fills the reference's constants: dt=0.1, Q=diag(0.1^2,0.1^2,(pi/180)^2,0.1^2), R=I. */
+void crb_ekf_default_params(crb_ekf_params* p);
+
+/* n agents, n_steps filter steps per launch (state stays in registers between steps).
+ *   x [4][n]  in/out   (px, py, yaw, v)
+ *   P [16][n] in/out   column-major 4x4
+ *   z [n_steps][2][n]  observations
+ *   u [n_steps][2][n]  controls (v, yaw-rate)
+ * Replaces: ekf_estimation(xEst, PEst, z, u, Q, R), src/extended_kalman_filter.cpp:64-78. */
+int crb_ekf_step_batched(crb_ctx* ctx, int64_t n, float* x, float* P, const float* z,
+                         const float* u, const crb_ekf_params* prm, int n_steps);
+int crb_ekf_step_batched_host(crb_ctx* ctx, int64_t n, float* x, float* P, const float* z,
+                              const float* u, const crb_ekf_params* prm, int n_steps);
+
+/* ---- particle filter -------------------------------------------------------------------------- */
+/* Constants from src/particle_filter.cpp: DT :18, PI :19 (3.141592653, *not* M_PI), Q :217 (0.01),
+ * Rsim :228-230.  rsim_diag are the two diagonal entries Rsim(0,0), Rsim(1,1) used at :87-88. */
+typedef struct crb_pf_params {
+  double dt;
+  double pi;       /* the reference's truncated PI literal */
+  float Q;         /* observation variance; sigma = sqrtf(Q) (:98) */
+  float rsim_diag[2];
+  float u[2];      /* shared control input */
+} crb_pf_params;
+void crb_pf_default_params(crb_pf_params* p);
+
+#define CRB_PF_MAX_LANDMARKS 64
+/*   px [4][n] in/out particles, pw [n] in/out weights
+ *   noise [2][n] standard-normal draws g1,g2 (the reference draws them as doubles from
+ *         std::normal_distribution<>, :87-88; here they are explicit f32 inputs), or NULL to draw
+ *         them in-kernel from Philox4x32-10(seed, particle index) + Box-Muller.
+ *   landmarks [n_lm][3] rows (range, lx, ly) exactly like the reference's z items (:263-266);
+ *         HOST pointer in both variants (tiny, copied to constant memory).
+ * Replaces: the particle loop of pf_localization, src/particle_filter.cpp:81-102. */
+int crb_pf_predict_weight_batched(crb_ctx* ctx, int64_t n, float* px, float* pw,
+                                  const float* noise, uint64_t seed, const float* landmarks,
+                                  int n_lm, const crb_pf_params* prm);
+int crb_pf_predict_weight_batched_host(crb_ctx* ctx, int64_t n, float* px, float* pw,
+                                       const float* noise, uint64_t seed, const float* landmarks,
+                                       int n_lm, const crb_pf_params* prm);
+/* Normalise weights, weighted mean and covariance (device pointers; outputs are HOST pointers).
+ *   pw is normalised in place (pw / pw.sum(), :104); xEst[4] = px * pw (:106);
+ *   PEst[16] (column-major) = sum_i pw_i (px_i - xEst)(px_i - xEst)^T (:59-71, :107).
+ * Reductions are done in double on the device (deterministic two-pass tree), so results are
+ * independent of the launch geometry.  sum_w_out (optional) receives the pre-normalisation sum. */
+int crb_pf_estimate(crb_ctx* ctx, int64_t n, const float* px, float* pw, float* xEst_host,
+                    float* PEst_host, double* sum_w_out_host);
+
+/* ---- MPC -------------------------------------------------------------------------------------- */
+/* Problem constants: src/model_predictive_control.cpp:23-48 (macros), cost weights :202-210 and
+ * :247-250, bounds :283-301.  T (number of stages incl. the initial state) is a call argument;
+ * the reference compiles T=6 (:24), BASELINE configs use T=20. */
+typedef struct crb_mpc_params {
+  float dt;            /* DT 0.2            :26 */
+  float wb;            /* WB 2.5            :36 */
+  float max_steer;     /* 45 deg            :27, bounds :288-291 */
+  float max_accel;     /* 1.0               :39, bounds :293-296 */
+  float max_speed;     /* 55/3.6            :37, bounds :298-301 */
+  float min_speed;     /* -20/3.6           :38 */
+  float w_a, w_delta;          /* 0.01, 0.01   input cost       :203-204 */
+  float w_da, w_ddelta;        /* 0.01, 1.0    input-rate cost  :208-209 */
+  float w_x, w_y, w_yaw, w_v;  /* 1, 1, 0.5, 0.5 tracking cost  :247-250 */
+  int   max_iter;      /* outer linearise-and-solve iterations; MAX_ITER 3 :30 is the reference macro */
+  float du_th;         /* stop when sum|du| <= du_th; DU_TH 0.1 :31 */
+  int   max_ls;        /* line-search halvings per iteration (no reference counterpart) */
+} crb_mpc_params;
+void crb_mpc_default_params(crb_mpc_params* p);
+
+#define CRB_MPC_MAX_T 32
+/* Per-agent status word (the reference drops IPOPT's status, :338-339). */
+#define CRB_MPC_CONVERGED     0  /* sum|du| <= du_th */
+#define CRB_MPC_MAX_ITER      1  /* iteration cap reached */
+#define CRB_MPC_NO_DESCENT    2  /* line search found no decrease (already at a stationary point) */
+#define CRB_MPC_NONFINITE     3  /* non-finite input or iterate */
+
+/*   x0   [4][n]      (x, y, yaw, v)                        <- State x0                     :255
+ *   xref [4*T][n]    field (4*t + k): stage t, component k <- M_XREF traj_ref (col-major)  :52,:255
+ *   u_init [2*(T-1)][n] warm start, fields [delta_0..delta_{T-2} | a_0..a_{T-2}], or NULL for the
+ *                    reference's cold start (all zeros, :266-269)
+ *   sol  [4T+2(T-1)][n] or NULL: the reference's return vector, fields in its order
+ *                    [x(T) | y(T) | yaw(T) | v(T) | delta(T-1) | a(T-1)]                   :54-60,:341-345
+ *   u0   [2][n] or NULL: (a_0, delta_0), the two values the caller consumes                :376
+ *   cost [n] or NULL: objective fg[0] at the returned point                                :199-250
+ *   status [n] or NULL: CRB_MPC_*;  iters [n] or NULL: executed outer iterations
+ * Replaces: mpc_solve(State x0, M_XREF traj_ref), src/model_predictive_control.cpp:255-346. */
+int crb_mpc_solve_batched(crb_ctx* ctx, int64_t n, int T, const float* x0, const float* xref,
+                          const float* u_init, const crb_mpc_params* prm, float* sol, float* u0,
+                          float* cost, int32_t* status, int32_t* iters);
+int crb_mpc_solve_batched_host(crb_ctx* ctx, int64_t n, int T, const float* x0, const float* xref,
+                               const float* u_init, const crb_mpc_params* prm, float* sol,
+                               float* u0, float* cost, int32_t* status, int32_t* iters);
+/* Plant step on the first control: state [4][n] in/out, u0 [2][n] = (a, delta).
+ * Replaces: update(State&, float a, float delta), src/model_predictive_control.cpp:69-81. */
+int crb_mpc_plant_update_batched(crb_ctx* ctx, int64_t n, float* state, const float* u0,
+                                 const crb_mpc_params* prm);
+/* Reference-trajectory lookup for every agent against one shared course.
+ *   course arrays cx, cy, cyaw, sp: DEVICE pointers, ncourse entries each
+ *   state [4][n]; target_ind [n] in/out (int32); xref [4*T][n] out
+ * Integer index work is bit-exact with the reference, including its quirks (float-typed index,
+ * :109; strict '<' first-minimum tie-break, :115; monotone target_ind, :139).  The reference reads
+ * cx[pind+9] without a bounds check (:110); here the search window is clipped to the course.
+ * Replaces: calc_ref_trajectory() :130-170 and calc_nearest_index() :107-127. */
+int crb_mpc_calc_ref_trajectory_batched(crb_ctx* ctx, int64_t n, int T, const float* state,
+                                        const float* cx, const float* cy, const float* cyaw,
+                                        const float* sp, int32_t ncourse, float dl,
+                                        int32_t* target_ind, float* xref,
+                                        const crb_mpc_params* prm);
+
+/* ---- summary statistics (the only inter-GPU payload) ------------------------------------------- */
+#define CRB_STATS_LEN 8
+/* Reduces a per-agent f32 array (and optional status / iteration arrays) on the device into
+ * stats_dev[CRB_STATS_LEN] (device pointer, f64):
+ *   [0] sum  [1] min  [2] max  [3] n_nonfinite  [4] n_status_converged  [5] sum_iters
+ *   [6] position-weighted checksum  sum_i value_i * ((i0+i) % 251 + 1)  [7] n
+ * i0 is the global index of this shard's first agent so that the checksum of a sharded run equals
+ * the single-GPU one.  The caller all-gathers the 8 doubles across ranks (NCCL). */
+int crb_stats_reduce(crb_ctx* ctx, int64_t n, int64_t i0, const float* values,
+                     const int32_t* status, const int32_t* iters, double* stats_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRB_H_ */

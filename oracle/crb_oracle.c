@@ -1,0 +1,298 @@
+/* crb_oracle.c — CPU restatement of the EKF and particle-filter hot paths of onlytailei/CppRobotics.
+ * TEST INFRASTRUCTURE ONLY (see crb_oracle.h for who may load it and for the parity-pinning note).
+ *
+ * Every function restates the cited reference lines with dense, textbook loops: the matrices are
+ * built in full (including their structural zeros and ones) and multiplied entry by entry in plain
+ * IEEE binary32 with separate multiply and add (build with -ffp-contract=off, no -mfma), which is
+ * what Eigen's fixed-size lazy products compile to on the reference's default x86-64 target.
+ * Column-major storage throughout, like Eigen: M(r,c) = M[r + rows*c].
+ */
+#include "crb_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+int crb_oracle_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+/* ---- tiny dense helpers ------------------------------------------------------------------------ */
+/* C(ra x cb) = A(ra x ca) * B(ca x cb); inner sum order selectable for ca == 4 */
+static void matmul(const float* A, int ra, int ca, const float* B, int cb, float* C, int order) {
+  for (int j = 0; j < cb; ++j) {
+    for (int i = 0; i < ra; ++i) {
+      float s;
+      if (order == CRB_ORDER_PAIRWISE && ca == 4) {
+        float s01 = A[i + ra * 0] * B[0 + ca * j] + A[i + ra * 1] * B[1 + ca * j];
+        float s23 = A[i + ra * 2] * B[2 + ca * j] + A[i + ra * 3] * B[3 + ca * j];
+        s = s01 + s23;
+      } else {
+        s = A[i + ra * 0] * B[0 + ca * j];
+        for (int k = 1; k < ca; ++k) s = s + A[i + ra * k] * B[k + ca * j];
+      }
+      C[i + ra * j] = s;
+    }
+  }
+}
+static void transpose(const float* A, int r, int c, float* At) {
+  for (int i = 0; i < r; ++i)
+    for (int j = 0; j < c; ++j) At[j + c * i] = A[i + r * j];
+}
+
+/* ---- motion_model: src/extended_kalman_filter.cpp:22-36 (same text at src/particle_filter.cpp:26-40)
+ *   F_ = I4 (:24-27)   B_ = [DT*cos(yaw) 0; DT*sin(yaw) 0; 0 DT; 1 0] (:29-33)   return F_*x + B_*u (:35)
+ * DT is a double literal, std::cos(float) returns float: entries are (float)(DT * (double)cosf()). */
+void crb_oracle_motion_model(const float x[4], const float u[2], double dt, float out[4]) {
+  float F[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  float B[8];
+  B[0 + 4 * 0] = (float)(dt * (double)cosf(x[2]));
+  B[1 + 4 * 0] = (float)(dt * (double)sinf(x[2]));
+  B[2 + 4 * 0] = (float)0.0;
+  B[3 + 4 * 0] = (float)1.0;
+  B[0 + 4 * 1] = 0.0f;
+  B[1 + 4 * 1] = 0.0f;
+  B[2 + 4 * 1] = (float)dt;
+  B[3 + 4 * 1] = (float)0.0;
+  float Fx[4], Bu[4];
+  matmul(F, 4, 4, x, 1, Fx, CRB_ORDER_SEQ);
+  matmul(B, 4, 2, u, 1, Bu, CRB_ORDER_SEQ);
+  for (int i = 0; i < 4; ++i) out[i] = Fx[i] + Bu[i];
+}
+
+/* ---- jacobF: src/extended_kalman_filter.cpp:38-47.  yaw = x(2), v = u(0) (:40-41);
+ *   jF(0,2) = -DT*v*sin(yaw)  jF(0,3) = DT*cos(yaw)  jF(1,2) = DT*v*cos(yaw)  jF(1,3) = DT*sin(yaw)
+ * evaluated left to right in double ((-DT*v)*sin) and narrowed on assignment. */
+void crb_oracle_jacobF(const float x[4], const float u[2], double dt, float jF[16]) {
+  for (int i = 0; i < 16; ++i) jF[i] = 0.0f;
+  for (int i = 0; i < 4; ++i) jF[i + 4 * i] = 1.0f;
+  float yaw = x[2];
+  float v = u[0];
+  jF[0 + 4 * 2] = (float)(-dt * (double)v * (double)sinf(yaw));
+  jF[0 + 4 * 3] = (float)(dt * (double)cosf(yaw));
+  jF[1 + 4 * 2] = (float)(dt * (double)v * (double)cosf(yaw));
+  jF[1 + 4 * 3] = (float)(dt * (double)sinf(yaw));
+}
+
+/* ---- ekf_estimation: src/extended_kalman_filter.cpp:64-78 ---------------------------------------- */
+void crb_oracle_ekf_estimation(float xEst[4], float PEst[16], const float z[2], const float u[2],
+                               const float Q[16], const float R[4], double dt, int order) {
+  float xPred[4], jF[16], jFt[16], T1[16], T2[16], PPred[16];
+  crb_oracle_motion_model(xEst, u, dt, xPred);                 /* :67 */
+  crb_oracle_jacobF(xPred, u, dt, jF);                         /* :68  (evaluated at xPred) */
+  transpose(jF, 4, 4, jFt);
+  matmul(jF, 4, 4, PEst, 4, T1, order);                        /* :69  (jF*PEst) */
+  matmul(T1, 4, 4, jFt, 4, T2, order);                         /*      (...)*jF^T */
+  for (int i = 0; i < 16; ++i) PPred[i] = T2[i] + Q[i];        /*      + Q */
+
+  float jH[8] = {1, 0, 0, 1, 0, 0, 0, 0};                      /* :57-62, 2x4 col-major */
+  float jHt[8];
+  transpose(jH, 2, 4, jHt);
+  float zPred[2];
+  matmul(jH, 2, 4, xPred, 1, zPred, CRB_ORDER_SEQ);            /* :72 observation_model :50-55 */
+  float y[2] = {z[0] - zPred[0], z[1] - zPred[1]};             /* :73 */
+  float HP[8], S[4];
+  matmul(jH, 2, 4, PPred, 4, HP, CRB_ORDER_SEQ);               /* :74 jH*PPred (selector: exact) */
+  matmul(HP, 2, 4, jHt, 2, S, CRB_ORDER_SEQ);
+  for (int i = 0; i < 4; ++i) S[i] = S[i] + R[i];
+  /* S.inverse(): Eigen's size-2 closed form, one division then four products */
+  float det = S[0] * S[3] - S[1] * S[2];
+  float invdet = 1.0f / det;
+  float Sinv[4];
+  Sinv[0] = S[3] * invdet;
+  Sinv[1] = -S[1] * invdet;
+  Sinv[2] = -S[2] * invdet;
+  Sinv[3] = S[0] * invdet;
+  float PHt[8], K[8];
+  matmul(PPred, 4, 4, jHt, 2, PHt, CRB_ORDER_SEQ);             /* :75 (PPred*jH^T) (selector: exact) */
+  matmul(PHt, 4, 2, Sinv, 2, K, CRB_ORDER_SEQ);                /*     (...)*S^-1 */
+  float Ky[4];
+  matmul(K, 4, 2, y, 1, Ky, CRB_ORDER_SEQ);                    /* :76 */
+  for (int i = 0; i < 4; ++i) xEst[i] = xPred[i] + Ky[i];
+  float KH[16], M[16];
+  matmul(K, 4, 2, jH, 4, KH, CRB_ORDER_SEQ);                   /* :77 K*jH */
+  for (int j = 0; j < 4; ++j)
+    for (int i = 0; i < 4; ++i) M[i + 4 * j] = (i == j ? 1.0f : 0.0f) - KH[i + 4 * j];
+  matmul(M, 4, 4, PPred, 4, PEst, order);                      /* (I-K*jH)*PPred, not symmetrised */
+}
+
+void crb_oracle_ekf_estimation_f64(double xEst[4], double PEst[16], const double z[2],
+                                   const double u[2], const double Q[16], const double R[4],
+                                   double dt) {
+  double xp[4], jF[16] = {0}, T1[16], PP[16];
+  double c = cos(xEst[2]), s = sin(xEst[2]);
+  xp[0] = xEst[0] + dt * c * u[0];
+  xp[1] = xEst[1] + dt * s * u[0];
+  xp[2] = xEst[2] + dt * u[1];
+  xp[3] = xEst[3] + u[0];
+  for (int i = 0; i < 4; ++i) jF[i + 4 * i] = 1.0;
+  jF[0 + 4 * 2] = -dt * u[0] * sin(xp[2]);
+  jF[0 + 4 * 3] = dt * cos(xp[2]);
+  jF[1 + 4 * 2] = dt * u[0] * cos(xp[2]);
+  jF[1 + 4 * 3] = dt * sin(xp[2]);
+  for (int j = 0; j < 4; ++j)
+    for (int i = 0; i < 4; ++i) {
+      double a = 0;
+      for (int k = 0; k < 4; ++k) a += jF[i + 4 * k] * PEst[k + 4 * j];
+      T1[i + 4 * j] = a;
+    }
+  for (int j = 0; j < 4; ++j)
+    for (int i = 0; i < 4; ++i) {
+      double a = 0;
+      for (int k = 0; k < 4; ++k) a += T1[i + 4 * k] * jF[j + 4 * k];
+      PP[i + 4 * j] = a + Q[i + 4 * j];
+    }
+  double y0 = z[0] - xp[0], y1 = z[1] - xp[1];
+  double S00 = PP[0] + R[0], S10 = PP[1] + R[1], S01 = PP[4] + R[2], S11 = PP[5] + R[3];
+  double det = S00 * S11 - S10 * S01;
+  double i00 = S11 / det, i10 = -S10 / det, i01 = -S01 / det, i11 = S00 / det;
+  double K[8];
+  for (int i = 0; i < 4; ++i) {
+    K[i] = PP[i] * i00 + PP[i + 4] * i10;
+    K[i + 4] = PP[i] * i01 + PP[i + 4] * i11;
+  }
+  for (int i = 0; i < 4; ++i) xEst[i] = xp[i] + K[i] * y0 + K[i + 4] * y1;
+  for (int j = 0; j < 4; ++j)
+    for (int i = 0; i < 4; ++i)
+      PEst[i + 4 * j] = PP[i + 4 * j] - (K[i] * PP[0 + 4 * j] + K[i + 4] * PP[1 + 4 * j]);
+}
+
+void crb_oracle_ekf_step_batched(int64_t n, float* x, float* P, const float* z, const float* u,
+                                 const float* Q, const float* R, double dt, int n_steps, int order,
+                                 int nthreads) {
+#ifdef _OPENMP
+  if (nthreads <= 0) nthreads = omp_get_max_threads();
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+#endif
+  for (int64_t i = 0; i < n; ++i) {
+    float xe[4], Pe[16], zz[2], uu[2];
+    for (int f = 0; f < 4; ++f) xe[f] = x[f * n + i];
+    for (int f = 0; f < 16; ++f) Pe[f] = P[f * n + i];
+    for (int s = 0; s < n_steps; ++s) {
+      zz[0] = z[((int64_t)s * 2 + 0) * n + i];
+      zz[1] = z[((int64_t)s * 2 + 1) * n + i];
+      uu[0] = u[((int64_t)s * 2 + 0) * n + i];
+      uu[1] = u[((int64_t)s * 2 + 1) * n + i];
+      crb_oracle_ekf_estimation(xe, Pe, zz, uu, Q, R, dt, order);
+    }
+    for (int f = 0; f < 4; ++f) x[f * n + i] = xe[f];
+    for (int f = 0; f < 16; ++f) P[f * n + i] = Pe[f];
+  }
+}
+
+/* ---- gauss_likelihood: src/particle_filter.cpp:53-57
+ *   float p = 1.0 / std::sqrt(2.0 * PI * sigma * sigma) * std::exp(-x * x / (2 * sigma * sigma));
+ * prefactor in double, exponent and exp in float (std::exp(float) -> expf), product in double. */
+float crb_oracle_gauss_likelihood(float x, float sigma, double pi) {
+  double pre = 1.0 / sqrt(2.0 * pi * (double)sigma * (double)sigma);
+  float e = expf(-x * x / (2 * sigma * sigma));
+  float p = (float)(pre * (double)e);
+  return p;
+}
+
+/* ---- one iteration of the particle loop: src/particle_filter.cpp:82-101 -------------------------- */
+void crb_oracle_pf_particle(float x[4], float* w, const double g[2], const float u[2],
+                            const float rsim_diag[2], const float* landmarks, int n_lm, float Q,
+                            double dt, double pi) {
+  float ud[2];
+  ud[0] = (float)((double)u[0] + g[0] * (double)rsim_diag[0]);   /* :87 */
+  ud[1] = (float)((double)u[1] + g[1] * (double)rsim_diag[1]);   /* :88 */
+  float xn[4];
+  crb_oracle_motion_model(x, ud, dt, xn);                          /* :90 */
+  float ww = *w;
+  for (int i = 0; i < n_lm; ++i) {                                 /* :92-99 */
+    const float* item = landmarks + 3 * i;                         /* (range, lx, ly) */
+    float dx = xn[0] - item[1];
+    float dy = xn[1] - item[2];
+    float prez = sqrtf(dx * dx + dy * dy);
+    float dz = prez - item[0];
+    ww = ww * crb_oracle_gauss_likelihood(dz, sqrtf(Q), pi);
+  }
+  for (int i = 0; i < 4; ++i) x[i] = xn[i];                        /* :100 */
+  *w = ww;                                                         /* :101 */
+}
+
+/* ---- counter-based normals (no reference counterpart: the reference copies an mt19937 by value,
+ * :78; the batched engine takes noise as an input array or draws it from Philox4x32-10) ---------- */
+static inline void philox_round(uint32_t c[4], const uint32_t k[2]) {
+  uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+  uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+  uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k[0];
+  uint32_t n1 = (uint32_t)p1;
+  uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k[1];
+  uint32_t n3 = (uint32_t)p0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+void crb_oracle_philox_normal2(uint64_t seed, uint64_t index, float g[2]) {
+  uint32_t c[4] = {(uint32_t)index, (uint32_t)(index >> 32), 0u, 0u};
+  uint32_t k[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k);
+    k[0] += 0x9E3779B9u;
+    k[1] += 0xBB67AE85u;
+  }
+  float u1 = (float)(c[0] >> 9) * 1.1920928955078125e-07f + 5.9604644775390625e-08f; /* (0,1) */
+  float u2 = (float)(c[1] >> 9) * 1.1920928955078125e-07f + 5.9604644775390625e-08f;
+  float rad = sqrtf(-2.0f * logf(u1));
+  float ang = 6.28318530717958647692f * u2;
+  g[0] = rad * cosf(ang);
+  g[1] = rad * sinf(ang);
+}
+
+void crb_oracle_pf_predict_weight_batched(int64_t n, float* px, float* pw, const float* noise,
+                                          uint64_t seed, const float* landmarks, int n_lm,
+                                          const float u[2], const float rsim_diag[2], float Q,
+                                          double dt, double pi, int nthreads) {
+#ifdef _OPENMP
+  if (nthreads <= 0) nthreads = omp_get_max_threads();
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+#endif
+  for (int64_t i = 0; i < n; ++i) {
+    float x[4], w = pw[i];
+    double g[2];
+    for (int f = 0; f < 4; ++f) x[f] = px[f * n + i];
+    if (noise) {
+      g[0] = (double)noise[i];
+      g[1] = (double)noise[n + i];
+    } else {
+      float gf[2];
+      crb_oracle_philox_normal2(seed, (uint64_t)i, gf);
+      g[0] = (double)gf[0];
+      g[1] = (double)gf[1];
+    }
+    crb_oracle_pf_particle(x, &w, g, u, rsim_diag, landmarks, n_lm, Q, dt, pi);
+    for (int f = 0; f < 4; ++f) px[f * n + i] = x[f];
+    pw[i] = w;
+  }
+}
+
+/* ---- pf_localization tail: src/particle_filter.cpp:104-107 and calc_covariance :59-71.
+ * The reference sums 100 floats in float; for 10^6 particles the batched engine accumulates in
+ * double (documented deviation), so this restatement does too. */
+void crb_oracle_pf_estimate(int64_t n, const float* px, float* pw, float xEst[4], float PEst[16],
+                            double* sum_w) {
+  double s = 0.0;
+  for (int64_t i = 0; i < n; ++i) s += (double)pw[i];
+  if (sum_w) *sum_w = s;
+  float sf = (float)s;
+  for (int64_t i = 0; i < n; ++i) pw[i] = pw[i] / sf;                 /* :104 */
+  double m[4] = {0, 0, 0, 0};
+  for (int64_t i = 0; i < n; ++i)
+    for (int f = 0; f < 4; ++f) m[f] += (double)px[f * n + i] * (double)pw[i];   /* :106 */
+  for (int f = 0; f < 4; ++f) xEst[f] = (float)m[f];
+  double C[16] = {0};
+  for (int64_t i = 0; i < n; ++i) {                                   /* :65-68 */
+    double d[4];
+    for (int f = 0; f < 4; ++f) d[f] = (double)(px[f * n + i] - xEst[f]);
+    for (int c = 0; c < 4; ++c)
+      for (int r = 0; r < 4; ++r) C[r + 4 * c] += (double)pw[i] * d[r] * d[c];
+  }
+  for (int k = 0; k < 16; ++k) PEst[k] = (float)C[k];
+}
