@@ -1,0 +1,545 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the batched hot paths on N B200s (one process per GPU).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ekf|pf|mpc]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+         --master-port P bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path over one batch of synthetic input (BASELINE.json configs):
+  ekf (headline, configs[1]): 2^20 agents x 1 EKF update per GPU          metric: EKF updates/s
+  pf  (configs[2]):           2^20 particles x 8 landmarks per GPU        metric: particle updates/s
+  mpc (configs[3]/[4]):       65 536 agents, T=20 per GPU                 metric: MPC solves/s
+The default run prints ONE JSON line whose headline is the EKF config; the PF and MPC configs are
+measured in the same run and reported under "extra" with their own roofline / cpu_baseline / e2e.
+Weak scaling: per-GPU work is fixed, shard r holds global indices [r*n, (r+1)*n) of the
+index-addressed generators; the only inter-GPU traffic is one all-gather of 8 doubles per rank.
+
+Timing rules followed: W >= 3 warm-up steps; inputs rotate over 3 buffer sets whose total exceeds the
+126 MB L2; device time from CUDA events on the launching stream, bracketed by barrier + synchronize,
+max over ranks; SM clocks sampled with nvidia-smi during the timed region.
+
+`--impl reference` times the CPU restatement of the reference (oracle/, the only implementation of the
+path that can run here: Eigen/IPOPT are absent) on the box's host cores with all threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+EKF_N = 1 << 20
+PF_N = 1 << 20
+PF_LM = 8
+MPC_N = 1 << 16
+MPC_T = 20
+MPC_ITER, MPC_DUTH, MPC_LS = 50, 1e-4, 8   # IPOPT's max_iter (:326); tight du so the NLP converges
+EKF_BYTES = 176       # read x4 P16 z2 u2, write x4 P16 (f32)            SURVEY §8 d-3
+PF_BYTES = 48         # read px4 w1 noise2, write px4 w1                  SURVEY §8 d-4
+MPC_BYTES = 344 + 472 # read x0 4 + xref 80, write sol 118 + u0 2 (+cost,status,iters 3) f32 ~ 828
+NSETS = 3
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)", d
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)", {}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [c.strip() for c in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx = max(mx, float(f[2]))
+            except ValueError:
+                continue
+            for k, nme in enumerate(names):
+                if f[4 + k].lower().startswith("active"):
+                    reasons.add(nme)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_setup(n_gpus: int):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    if world != n_gpus:
+        raise SystemExit(f"--gpus {n_gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    return rank, world, local
+
+
+def barrier_sync(world):
+    import torch
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(ms: float, world: int) -> float:
+    import torch
+    if world == 1:
+        return ms
+    import torch.distributed as dist
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def gather_stats(stats, world):
+    """The single collective of the data path: all-gather of CRB_STATS_LEN doubles per rank."""
+    import torch
+    if world == 1:
+        return stats.unsqueeze(0)
+    import torch.distributed as dist
+    out = torch.empty((world, stats.numel()), dtype=stats.dtype, device=stats.device)
+    dist.all_gather_into_tensor(out, stats)
+    return out
+
+
+def pinned(a):
+    import torch
+    t = torch.from_numpy(a).pin_memory()
+    return t
+
+
+# =========================================================================================================
+# workloads: each returns a dict with value / ms_per_step / roofline / e2e / cpu_baseline pieces
+# =========================================================================================================
+def time_device_steps(step_fn, steps, warmup, world, after_fn=None):
+    """W untimed + K timed steps between barrier+sync brackets; CUDA events on the current stream."""
+    import torch
+    for k in range(warmup):
+        step_fn(k)
+    barrier_sync(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(steps):
+        step_fn(warmup + k)
+    if after_fn is not None:
+        after_fn()
+    e1.record()
+    barrier_sync(world)
+    return max_over_ranks(e0.elapsed_time(e1), world)
+
+
+def time_host_steps(step_fn, steps, warmup, world):
+    import torch
+    for k in range(max(1, min(warmup, 2))):
+        step_fn(k)
+    barrier_sync(world)
+    t0 = time.perf_counter()
+    for k in range(steps):
+        step_fn(k)
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3
+    barrier_sync(world)
+    return max_over_ranks(ms, world)
+
+
+def cpu_time(fn, units_per_call, budget_s=6.0, min_calls=2):
+    """Bounded CPU sample: repeat fn until ~budget_s of wall time; returns units/s."""
+    fn()  # warm caches / thread pool
+    t0 = time.perf_counter()
+    calls = 0
+    while True:
+        fn()
+        calls += 1
+        el = time.perf_counter() - t0
+        if calls >= min_calls and el >= budget_s:
+            break
+        if el > 4 * budget_s:
+            break
+    return units_per_call * calls / el, calls, el
+
+
+def bench_ekf(eng, rank, world, steps, warmup, with_cpu):
+    import torch
+    from cpprobotics_b200 import synth
+    n = EKF_N
+    dev = torch.device("cuda", torch.cuda.current_device())
+    host = synth.ekf_inputs(n, i0=rank * n)
+    sets = []
+    for s in range(NSETS):   # identical contents, distinct memory: only residency matters
+        sets.append(tuple(torch.from_numpy(a).to(dev) for a in host))
+    stats = torch.zeros(8, dtype=torch.float64, device=dev)
+    l0 = eng.launches
+
+    def step(k):
+        x, P, z, u = sets[k % NSETS]
+        eng.ekf_estimation(x, P, z, u)
+
+    def after():
+        eng.stats_reduce(sets[0][0][0], i0=rank * n, out=stats)   # summary of the x field
+        gather_stats(stats, world)
+
+    for k in range(warmup):
+        step(k)
+    l0 = eng.launches
+    ms = time_device_steps(step, steps, 0, world, after)
+    launches = eng.launches - l0
+    value = world * n * steps / (ms * 1e-3)
+    # roofline of the dominant kernel (one launch per step): algorithmic bytes / avg launch duration.
+    # measured separately WITHOUT the stats tail so that it is the kernel alone.
+    ms_k = time_device_steps(step, steps, 3, world)
+    peak, peak_src, _ = peaks()
+    achieved = EKF_BYTES * n * steps / (ms_k * 1e-3) / 1e9
+    # e2e through the host-pointer C-ABI entry: pinned host buffers, H2D + kernel + D2H every step
+    hx, hP, hz, hu = (pinned(a) for a in host)
+    ms_e = time_host_steps(lambda k: eng.ekf_estimation_host(hx, hP, hz, hu), max(3, min(steps, 10)),
+                           warmup, world)
+    e_steps = max(3, min(steps, 10))
+    out = dict(value=value, ms=ms / steps, launches=launches,
+               roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s",
+                             frac=achieved / peak, traffic=traffic_for("ekf"), peak_source=peak_src,
+                             kernel="crb_ekf_step_kernel",
+                             algorithmic_bytes_per_launch=EKF_BYTES * n),
+               e2e=dict(value=world * n * e_steps / (ms_e * 1e-3), unit="updates/s",
+                        h2d_bytes_per_step=96 * n, d2h_bytes_per_step=80 * n))
+    if with_cpu and rank == 0:
+        out["cpu_baseline"] = cpu_ekf(host)
+    return out
+
+
+def cpu_ekf(host=None):
+    from cpprobotics_b200 import synth
+    from oracle import oracle as O
+    n = EKF_N
+    x, P, z, u = host if host is not None else synth.ekf_inputs(n)
+    x, P = x.copy(), P.copy()
+    thr = O.num_threads()
+    v, calls, el = cpu_time(lambda: O.ekf_step_batched(x, P, z, u, nthreads=thr, inplace=True), n,
+                            budget_s=5.0)
+    return dict(value=v, unit="updates/s", cores=thr, kind="port",
+                sample=f"{calls} x {n} agents x 1 step, oracle/crb_oracle.c -O2 -ffp-contract=off, "
+                       f"OpenMP {thr} threads, {el:.1f} s")
+
+
+def bench_pf(eng, rank, world, steps, warmup, with_cpu):
+    import torch
+    from cpprobotics_b200 import synth
+    n = PF_N
+    dev = torch.device("cuda", torch.cuda.current_device())
+    host = synth.pf_inputs(n, i0=rank * n, n_total=world * n)
+    lm = synth.pf_landmarks(PF_LM)
+    sets = [tuple(torch.from_numpy(a).to(dev) for a in host) for _ in range(NSETS + 3)]  # 6 x 29 MB
+
+    def step(k):
+        px, pw, noise = sets[k % len(sets)]
+        pw.fill_(1.0 / (world * n))     # keep weights in the normal range across repeated steps
+        eng.pf_predict_weight(px, pw, noise, lm)
+
+    def step_nofill(k):
+        px, pw, noise = sets[k % len(sets)]
+        eng.pf_predict_weight(px, pw, noise, lm)
+
+    ms_k = time_device_steps(step_nofill, steps, warmup, world)
+    value = world * n * steps / (ms_k * 1e-3)
+    peak, peak_src, _ = peaks()
+    achieved = PF_BYTES * n * steps / (ms_k * 1e-3) / 1e9
+    hpx, hpw, hno = (pinned(a) for a in host)
+    e_steps = max(3, min(steps, 10))
+    ms_e = time_host_steps(lambda k: eng.pf_predict_weight_host(hpx, hpw, hno, lm), e_steps, warmup,
+                           world)
+    out = dict(metric="PF particle updates/sec (predict+weight, 8 landmarks)", value=value,
+               unit="particles/s", ms_per_step=ms_k / steps,
+               config=dict(workload="pf_predict_weight_2^20_particles_8_landmarks_per_gpu",
+                           l2=f"{len(sets)} rotating buffer sets, {len(sets) * 29} MB > 126 MB L2"),
+               roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s",
+                             frac=achieved / peak, traffic=traffic_for("pf"), peak_source=peak_src,
+                             kernel="crb_pf_predict_weight_kernel",
+                             algorithmic_bytes_per_launch=PF_BYTES * n),
+               e2e=dict(value=world * n * e_steps / (ms_e * 1e-3), unit="particles/s",
+                        h2d_bytes_per_step=28 * n, d2h_bytes_per_step=20 * n))
+    if with_cpu and rank == 0:
+        out["cpu_baseline"] = cpu_pf(host, lm)
+    return out
+
+
+def cpu_pf(host=None, lm=None):
+    from cpprobotics_b200 import synth
+    from oracle import oracle as O
+    n = PF_N
+    px, pw, noise = host if host is not None else synth.pf_inputs(n)
+    lm = lm if lm is not None else synth.pf_landmarks(PF_LM)
+    px, pw0 = px.copy(), pw.copy()
+    thr = O.num_threads()
+
+    def one():
+        pw[:] = pw0          # keep the weights in the normal range across repeated steps
+        O.pf_predict_weight_batched(px, pw, noise, lm, nthreads=thr, inplace=True)
+    pw = pw0.copy()
+    v, calls, el = cpu_time(one, n, budget_s=4.0)
+    return dict(value=v, unit="particles/s", cores=thr, kind="port",
+                sample=f"{calls} x {n} particles x {PF_LM} landmarks, oracle/crb_oracle.c, OpenMP {thr} "
+                       f"threads, {el:.1f} s")
+
+
+def mpc_flops(iters_sum, n, T):
+    """Executed-work flop model: per outer iteration one backward sweep (~470 flop /
+    stage, structured) and ~1.2 forward sweeps (~150 flop / stage incl. polynomial sin/cos)."""
+    return iters_sum * (T - 1) * (470.0 + 1.2 * 150.0)
+
+
+def bench_mpc(eng, rank, world, steps, warmup, with_cpu):
+    import torch
+    from cpprobotics_b200 import mpc_default_params, synth
+    n, T = MPC_N, MPC_T
+    dev = torch.device("cuda", torch.cuda.current_device())
+    course = synth.mpc_course()
+    st, pind = synth.mpc_states(n, i0=rank * n, course=course)
+    xref, _ = synth.mpc_xref_numpy(st, pind, T, course=course)
+    prm = mpc_default_params()
+    prm.max_iter, prm.du_th, prm.max_ls = MPC_ITER, MPC_DUTH, MPC_LS
+    nsol = 4 * T + 2 * (T - 1)
+    sets = [(torch.from_numpy(st).to(dev), torch.from_numpy(xref).to(dev)) for _ in range(NSETS)]
+    sol = torch.empty((nsol, n), dtype=torch.float32, device=dev)
+    u0 = torch.empty((2, n), dtype=torch.float32, device=dev)
+    cost = torch.empty(n, dtype=torch.float32, device=dev)
+    status = torch.empty(n, dtype=torch.int32, device=dev)
+    iters = torch.empty(n, dtype=torch.int32, device=dev)
+    stats = torch.zeros(8, dtype=torch.float64, device=dev)
+    gathered = {}
+
+    def step(k):
+        s, xr = sets[k % NSETS]
+        eng.mpc_solve(s, xr, T, prm, sol=sol, u0=u0, cost=cost, status=status, iters=iters)
+        eng.stats_reduce(cost, status, iters, i0=rank * n, out=stats)
+        gathered["g"] = gather_stats(stats, world)   # config 5: NCCL gather of cost stats per call
+
+    def step_kernel_only(k):
+        s, xr = sets[k % NSETS]
+        eng.mpc_solve(s, xr, T, prm, sol=sol, u0=u0, cost=cost, status=status, iters=iters)
+
+    ms = time_device_steps(step, steps, warmup, world)
+    value = world * n * steps / (ms * 1e-3)
+    ms_k = time_device_steps(step_kernel_only, steps, 1, world)
+    g = gathered["g"].cpu().numpy()
+    iters_sum = float(g[:, 5].sum())
+    # governing roofline: the solver's working set (trajectories + gains, 502 floats/problem) streams
+    # through L2/HBM once per sweep, so both an HBM figure (algorithmic I/O bytes) and the executed
+    # flop rate are reported; fp32 peak = SMs x 128 lanes x 2 x max SM clock.
+    peak, peak_src, pk = peaks()
+    achieved = MPC_BYTES * n * steps / (ms_k * 1e-3) / 1e9
+    sm_max = float(pk.get("sm_max_mhz", 1965.0))
+    fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+    tfl = mpc_flops(iters_sum / world, n, T) * steps / (ms_k * 1e-3) / 1e12
+    hst, hxr = pinned(st), pinned(xref)
+    hsol = torch.empty((nsol, n), dtype=torch.float32).pin_memory()
+    hu0 = torch.empty((2, n), dtype=torch.float32).pin_memory()
+    hcost = torch.empty(n, dtype=torch.float32).pin_memory()
+    hstat = torch.empty(n, dtype=torch.int32).pin_memory()
+    hit = torch.empty(n, dtype=torch.int32).pin_memory()
+    e_steps = max(2, min(steps, 5))
+    ms_e = time_host_steps(lambda k: eng.mpc_solve_host(hst, hxr, T, prm, sol=hsol, u0=hu0, cost=hcost,
+                                                        status=hstat, iters=hit), e_steps, 1, world)
+    out = dict(metric="MPC solves/sec (T=20, bicycle model, box-constrained DDP to NLP convergence)",
+               value=value, unit="solves/s", ms_per_step=ms / steps,
+               config=dict(workload="mpc_T20_65536_agents_per_gpu", max_iter=MPC_ITER, du_th=MPC_DUTH,
+                           max_ls=MPC_LS, stats_allgather="every step",
+                           l2="3 rotating input sets; solver workspace 131 MB > 126 MB L2"),
+               solver=dict(mean_iters=iters_sum / (world * n),
+                           frac_converged=float(g[:, 4].sum()) / (world * n),
+                           mean_cost=float(g[:, 0].sum()) / (world * n),
+                           checksum=float(g[:, 6].sum())),
+               roofline=dict(bound="fp32", achieved=tfl, peak=fp32_peak, unit="TFLOP/s",
+                             frac=tfl / fp32_peak, traffic=traffic_for("mpc"),
+                             peak_source=f"148 SM x 128 FMA lanes x 2 x {sm_max:.0f} MHz (nominal; "
+                                         "MEASURED_PEAKS.json has no fp32 non-tensor figure)",
+                             kernel="crb_mpc_solve_kernel", flop_model="see DESIGN.md",
+                             io_gbs=achieved, io_frac_of_hbm=achieved / peak),
+               e2e=dict(value=world * n * e_steps / (ms_e * 1e-3), unit="solves/s",
+                        h2d_bytes_per_step=(4 + 4 * T) * 4 * n, d2h_bytes_per_step=(nsol + 5) * 4 * n))
+    if with_cpu and rank == 0:
+        out["cpu_baseline"] = cpu_mpc(st, xref)
+    return out
+
+
+def cpu_mpc(st=None, xref=None, sample=8192):
+    from cpprobotics_b200 import synth
+    from oracle import oracle as O
+    T = MPC_T
+    if st is None:
+        course = synth.mpc_course()
+        st, pind = synth.mpc_states(sample, course=course)
+        xref, _ = synth.mpc_xref_numpy(st, pind, T, course=course)
+    st, xref = np.ascontiguousarray(st[:, :sample]), np.ascontiguousarray(xref[:, :sample])
+    thr = O.num_threads()
+    prm = O.mpc_params(max_iter=MPC_ITER, du_th=MPC_DUTH, max_ls=MPC_LS)
+    v, calls, el = cpu_time(lambda: O.mpc_solve_batched(st, xref, T, prm, nthreads=thr), sample,
+                            budget_s=5.0)
+    return dict(value=v, unit="solves/s", cores=thr, kind="port",
+                sample=f"{calls} x {sample} agents (first {sample} of the GPU batch), T={T}, "
+                       f"oracle/crb_oracle_mpc.c same algorithm, OpenMP {thr} threads, {el:.1f} s; "
+                       "the reference's CppAD+IPOPT solve cannot be built here (its own budget is "
+                       "50 ms per solve, model_predictive_control.cpp:328)")
+
+
+def traffic_for(name):
+    """DRAM bytes per launch from the committed ncu --set full capture (profiles/traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(name)
+        except Exception:
+            return None
+    return None
+
+
+# =========================================================================================================
+def run_ours(args):
+    import torch
+    from cpprobotics_b200 import Engine
+    rank, world, local = dist_setup(args.gpus)
+    eng = Engine(local)
+    res = {}
+    with ClockSampler(local) as clk:
+        head = bench_ekf(eng, rank, world, args.steps, args.warmup, with_cpu=not args.no_cpu)
+        if args.workload in ("all", "pf"):
+            res["pf"] = bench_pf(eng, rank, world, args.steps, args.warmup, with_cpu=not args.no_cpu)
+        if args.workload in ("all", "mpc"):
+            res["mpc"] = bench_mpc(eng, rank, world, max(3, args.steps // 5), max(1, args.warmup // 3),
+                                   with_cpu=not args.no_cpu)
+    line = {
+        "metric": "EKF updates/sec (4-state/2-obs predict+update, batched)",
+        "value": head["value"], "unit": "updates/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": head["ms"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "ekf_2^20_agents_1_step_per_gpu (BASELINE.json configs[1])",
+                   "agents_per_gpu": EKF_N, "global_agents": EKF_N * world,
+                   "l2": "3 rotating buffer sets, 303 MB of inputs > 126 MB L2",
+                   "collective": "one all-gather of 8 doubles per rank inside the timed region"},
+        "clocks": clk.summary(), "e2e": head["e2e"], "gpu_launches": head["launches"],
+        "roofline": head["roofline"],
+    }
+    if "cpu_baseline" in head:
+        line["cpu_baseline"] = head["cpu_baseline"]
+    if res:
+        line["extra"] = res
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    """The reference's CPU implementation of the path on the host cores (the oracle port: the real
+    Eigen / CppAD / IPOPT sources cannot be built in this image).  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    from cpprobotics_b200 import synth
+    n = EKF_N
+    x, P, z, u = synth.ekf_inputs(n)
+    thr = O.num_threads()
+    for _ in range(args.warmup):
+        O.ekf_step_batched(x, P, z, u, nthreads=thr, inplace=True)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.ekf_step_batched(x, P, z, u, nthreads=thr, inplace=True)
+    el = time.perf_counter() - t0
+    v = n * args.steps / el
+    line = {
+        "impl": "reference", "metric": "EKF updates/sec (4-state/2-obs predict+update, batched)",
+        "value": v, "unit": "updates/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "ekf_2^20_agents_1_step_per_gpu (BASELINE.json configs[1])",
+                   "agents_per_gpu": EKF_N},
+        "cpu_baseline": {"value": v, "unit": "updates/s", "cores": thr, "kind": "port",
+                         "sample": f"{args.steps} x {n} agents x 1 step per timed step, oracle/crb_oracle.c "
+                                   f"(-O2 -ffp-contract=off), OpenMP {thr} threads"},
+        "e2e": {"value": v, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    if args.workload in ("all", "pf"):
+        line.setdefault("extra", {})["pf"] = cpu_pf()
+    if args.workload in ("all", "mpc"):
+        line.setdefault("extra", {})["mpc"] = cpu_mpc()
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="all", choices=["all", "ekf", "pf", "mpc"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

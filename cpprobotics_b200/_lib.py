@@ -48,6 +48,7 @@ PROTOTYPES = {
     "crb_init": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
     "crb_destroy": (C.c_int, [C.c_void_p]),
     "crb_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "crb_use_own_stream": (C.c_int, [C.c_void_p]),
     "crb_get_stream": (C.c_void_p, [C.c_void_p]),
     "crb_sync": (C.c_int, [C.c_void_p]),
     "crb_launch_count": (C.c_int64, [C.c_void_p]),

@@ -56,6 +56,7 @@ int crb_destroy(crb_ctx* ctx) {
   if (!ctx) return CRB_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(ctx->own_stream);
   for (int i = 0; i < CRB_N_PIPE; ++i) {
     cudaStreamSynchronize(ctx->pipe_stream[i]);
     if (ctx->pipe_buf[i]) cudaFree(ctx->pipe_buf[i]);
@@ -73,7 +74,12 @@ int crb_destroy(crb_ctx* ctx) {
 
 int crb_set_stream(crb_ctx* ctx, void* cuda_stream) {
   CRB_REQUIRE(ctx != nullptr, "ctx is NULL");
-  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  ctx->stream = (cudaStream_t)cuda_stream;
+  return CRB_OK;
+}
+int crb_use_own_stream(crb_ctx* ctx) {
+  CRB_REQUIRE(ctx != nullptr, "ctx is NULL");
+  ctx->stream = ctx->own_stream;
   return CRB_OK;
 }
 void* crb_get_stream(crb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
@@ -172,9 +178,9 @@ void crb_mpc_default_params(crb_mpc_params* p) {
   p->w_y = 1.0f;
   p->w_yaw = 0.5f;
   p->w_v = 0.5f;
-  p->max_iter = 3;
-  p->du_th = 0.1f;
-  p->max_ls = 6;
+  p->max_iter = 50;   // IPOPT's max_iter option (:326); MAX_ITER 3 / DU_TH 0.1 (:30-31) are unused macros
+  p->du_th = 1.0e-4f;
+  p->max_ls = 8;
 }
 
 }  // extern "C"

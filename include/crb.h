@@ -62,9 +62,11 @@ const char* crb_last_error_string(void);
 /* device_id < 0 -> current device.  Creates a private non-blocking stream. */
 int crb_init(crb_ctx** out, int device_id);
 int crb_destroy(crb_ctx* ctx);
-/* Use a caller-provided cudaStream_t (e.g. torch's current stream) instead of the private one;
- * stream == NULL restores the private stream. */
+/* Enqueue on a caller-provided cudaStream_t (e.g. torch's current stream) instead of the private
+ * one.  The handle is used verbatim: NULL is CUDA's legacy default stream, not "none".
+ * crb_use_own_stream() goes back to the context's private stream. */
 int crb_set_stream(crb_ctx* ctx, void* cuda_stream);
+int crb_use_own_stream(crb_ctx* ctx);
 void* crb_get_stream(crb_ctx* ctx);
 int crb_sync(crb_ctx* ctx);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
@@ -152,9 +154,11 @@ typedef struct crb_mpc_params {
   float w_a, w_delta;          /* 0.01, 0.01   input cost       :203-204 */
   float w_da, w_ddelta;        /* 0.01, 1.0    input-rate cost  :208-209 */
   float w_x, w_y, w_yaw, w_v;  /* 1, 1, 0.5, 0.5 tracking cost  :247-250 */
-  int   max_iter;      /* outer linearise-and-solve iterations; MAX_ITER 3 :30 is the reference macro */
-  float du_th;         /* stop when sum|du| <= du_th; DU_TH 0.1 :31 */
-  int   max_ls;        /* line-search halvings per iteration (no reference counterpart) */
+  int   max_iter;      /* cap on outer linearise-and-solve iterations; default 50 = the max_iter the
+                          reference gives IPOPT (:326).  (MAX_ITER 3 :30 and DU_TH 0.1 :31 are macros the
+                          reference defines but never uses.) */
+  float du_th;         /* stop when sum_t |du_t| <= du_th; default 1e-4 (converged to the NLP optimum) */
+  int   max_ls;        /* step halvings per iteration, default 8 (no reference counterpart) */
 } crb_mpc_params;
 void crb_mpc_default_params(crb_mpc_params* p);
 

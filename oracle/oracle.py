@@ -96,11 +96,13 @@ def ekf_estimation_f64(xEst, PEst, z, u, Q=None, R=None, dt=None):
     return x, P
 
 
-def ekf_step_batched(x, P, z, u, Q=None, R=None, dt=None, n_steps=1, order=ORDER_SEQ, nthreads=0):
-    """SoA batch with the libcrb layout; returns new (x, P)."""
+def ekf_step_batched(x, P, z, u, Q=None, R=None, dt=None, n_steps=1, order=ORDER_SEQ, nthreads=0,
+                     inplace=False):
+    """SoA batch with the libcrb layout; returns new (x, P) (copies unless inplace)."""
     d, Qd, Rd = ekf_constants()
-    x = np.ascontiguousarray(x, np.float32).copy()
-    P = np.ascontiguousarray(P, np.float32).copy()
+    if not inplace:
+        x = np.ascontiguousarray(x, np.float32).copy()
+        P = np.ascontiguousarray(P, np.float32).copy()
     n = x.shape[1]
     lib().crb_oracle_ekf_step_batched(n, x, P, np.ascontiguousarray(z, np.float32),
                                       np.ascontiguousarray(u, np.float32),
@@ -121,10 +123,12 @@ def philox_normal2(seed, index):
     return g
 
 
-def pf_predict_weight_batched(px, pw, noise, landmarks, seed=0, consts=None, nthreads=0):
+def pf_predict_weight_batched(px, pw, noise, landmarks, seed=0, consts=None, nthreads=0,
+                              inplace=False):
     c = consts or pf_constants()
-    px = np.ascontiguousarray(px, np.float32).copy()
-    pw = np.ascontiguousarray(pw, np.float32).copy()
+    if not inplace:
+        px = np.ascontiguousarray(px, np.float32).copy()
+        pw = np.ascontiguousarray(pw, np.float32).copy()
     lm = np.ascontiguousarray(np.asarray(landmarks, np.float32).reshape(-1, 3))
     nptr = None
     if noise is not None:
