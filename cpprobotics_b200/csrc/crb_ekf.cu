@@ -16,6 +16,8 @@
 // (sequential-k) order and with separate multiply and add (this TU is compiled with -fmad=false; the
 // kernel is memory-bound, FMUL+FADD instead of FFMA costs nothing).  With that, results differ from
 // the CPU restatement only through sinf/cosf (CUDA vs glibc, <= 2 ulp).
+#include <stdlib.h>
+
 #include "crb_common.cuh"
 
 struct EkfArgs {
@@ -97,7 +99,8 @@ __device__ __forceinline__ void ekf_step(float (&x)[4], float (&P)[16], float z0
 
 // count agents, leading dimension ld (>= count) for x/P, ld_zu for z/u (they may live in a staging
 // buffer with a different pitch).
-__global__ void __launch_bounds__(256)
+template <int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB)
 crb_ekf_step_kernel(int64_t count, int64_t ld, float* __restrict__ x, float* __restrict__ P,
                     const float* __restrict__ z, const float* __restrict__ u, int64_t ld_zu,
                     int n_steps, EkfArgs a) {
@@ -135,9 +138,30 @@ static int ekf_launch(crb_ctx* ctx, cudaStream_t st, int64_t count, int64_t ld, 
   a.dt = prm->dt;
   memcpy(a.Q, prm->Q, sizeof(a.Q));
   memcpy(a.R, prm->R, sizeof(a.R));
-  const int block = 256;
-  crb_ekf_step_kernel<<<crb_grid_for(count, block), block, 0, st>>>(count, ld, x, P, z, u, ld_zu,
-                                                                    n_steps, a);
+  // Launch shape: 256-thread CTAs, 4 resident per SM (64 registers): 32 warps x 24 independent
+  // 128-byte loads in flight per SM.  CRB_EKF_VARIANT selects alternatives for A/B measurements.
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("CRB_EKF_VARIANT");
+    variant = e ? atoi(e) : 0;
+  }
+  switch (variant) {
+    case 1:
+      crb_ekf_step_kernel<256, 3><<<crb_grid_for(count, 256), 256, 0, st>>>(count, ld, x, P, z, u,
+                                                                            ld_zu, n_steps, a);
+      break;
+    case 2:
+      crb_ekf_step_kernel<128, 8><<<crb_grid_for(count, 128), 128, 0, st>>>(count, ld, x, P, z, u,
+                                                                            ld_zu, n_steps, a);
+      break;
+    case 3:
+      crb_ekf_step_kernel<512, 2><<<crb_grid_for(count, 512), 512, 0, st>>>(count, ld, x, P, z, u,
+                                                                            ld_zu, n_steps, a);
+      break;
+    default:
+      crb_ekf_step_kernel<256, 4><<<crb_grid_for(count, 256), 256, 0, st>>>(count, ld, x, P, z, u,
+                                                                            ld_zu, n_steps, a);
+  }
   CRB_CUDA(cudaGetLastError());
   ctx->launches++;
   return CRB_OK;

@@ -9,9 +9,10 @@
 // and-solve replacing IPOPT"): box-constrained DDP on the reference NLP.  Each outer iteration
 // linearises the dynamics :242-245 along the current roll-out (with their exact second derivatives),
 // runs a Riccati recursion on the (state, previous input) augmented system so that the input-rate
-// cost :207-210 is handled exactly, solves the 2-D box QP of every stage in closed form (|delta|,
-// |a| and the speed limits :288-301 folded into a bound on a_t), and rolls the clamped non-linear
-// dynamics forward with step halving until the cost decreases.  The executable specification is
+// cost :207-210 is handled exactly, takes a projected-Newton step of the 2-D box QP of every stage in
+// closed form (|delta|, |a| and the speed limits :288-301 folded into a bound on a_t; the stage
+// Hessian may be indefinite), and rolls the clamped non-linear dynamics forward with step halving until the cost decreases
+// (one Gauss-Newton retry if the Newton direction gives no decrease).  The executable specification is
 // oracle/crb_oracle_mpc.c; this kernel reproduces it BIT FOR BIT (explicit fmaf, -fmad=false,
 // polynomial sin/cos, IEEE divide/sqrt), so status words and iteration counts match exactly.
 //
@@ -104,22 +105,62 @@ __device__ __forceinline__ void dyn_step(const float (&x)[4], float delta, float
   xn[3] = fmaf(a, p.dt, x[3]);
 }
 
-// Exact minimiser of 0.5 u'Hu + g'u over a 2-D box (see box_qp2 in the oracle).
-__device__ __forceinline__ void box_qp2(float H00, float H01, float H11, float g0, float g1,
-                                        float lo0, float lo1, float hi0, float hi1, float idet,
-                                        float ih00, float ih11, float& k0, float& k1, bool& cl0,
-                                        bool& cl1) {
+struct QpResult {
+  float k0, k1;
+  bool cl0, cl1;
+  float H00, H11;  // regularised diagonal used for the gains (H01 is never changed)
+  float idet, ih00, ih11;
+};
+
+// Projected-Newton step of the 2-D box QP (see box_qp2 in the oracle: same operations, same order).
+__device__ __forceinline__ void box_qp2(float Q00, float Q01, float Q11, float g0, float g1,
+                                        float lo0, float lo1, float hi0, float hi1, QpResult& r) {
+  const bool sa0lo = lo0 >= 0.0f && g0 > 0.0f, sa0hi = !sa0lo && hi0 <= 0.0f && g0 < 0.0f;
+  const bool sa1lo = lo1 >= 0.0f && g1 > 0.0f, sa1hi = !sa1lo && hi1 <= 0.0f && g1 < 0.0f;
+  const bool sa0 = sa0lo || sa0hi, sa1 = sa1lo || sa1hi;
+  r.H00 = Q00; r.H11 = Q11; r.idet = 0.0f; r.ih00 = 0.0f; r.ih11 = 0.0f;
+  r.k0 = 0.0f; r.k1 = 0.0f;
+  if (sa0) r.k0 = sa0lo ? lo0 : hi0;
+  if (sa1) r.k1 = sa1lo ? lo1 : hi1;
+  if (sa0 && sa1) { r.cl0 = true; r.cl1 = true; return; }
+  if (sa0) {
+    r.H11 = Q11 > REG_EPS ? Q11 : REG_EPS;
+    r.ih11 = 1.0f / r.H11;
+    float uj = -(fmaf(Q01, r.k0, g1) * r.ih11);
+    bool cj = false;
+    if (uj <= lo1) { uj = lo1; cj = true; }
+    else if (uj >= hi1) { uj = hi1; cj = true; }
+    r.k1 = uj; r.cl0 = true; r.cl1 = cj;
+    return;
+  }
+  if (sa1) {
+    r.H00 = Q00 > REG_EPS ? Q00 : REG_EPS;
+    r.ih00 = 1.0f / r.H00;
+    float uj = -(fmaf(Q01, r.k1, g0) * r.ih00);
+    bool cj = false;
+    if (uj <= lo0) { uj = lo0; cj = true; }
+    else if (uj >= hi0) { uj = hi0; cj = true; }
+    r.k0 = uj; r.cl1 = true; r.cl0 = cj;
+    return;
+  }
+  const float mh = 0.5f * (Q00 + Q11), dh = 0.5f * (Q00 - Q11);
+  const float lam = mh - sqrtf(fmaf(dh, dh, Q01 * Q01));
+  const float shift = lam < REG_EPS ? REG_EPS - lam : 0.0f;
+  const float H00 = Q00 + shift, H11 = Q11 + shift, H01 = Q01;
+  const float det = fmaf(H00, H11, -(H01 * H01));
+  const float idet = 1.0f / det, ih00 = 1.0f / H00, ih11 = 1.0f / H11;
+  r.H00 = H00; r.H11 = H11; r.idet = idet; r.ih00 = ih00; r.ih11 = ih11;
   const float n0 = fmaf(H01, g1, -(H11 * g0));
   const float n1 = fmaf(H01, g0, -(H00 * g1));
   const float u0 = n0 * idet, u1 = n1 * idet;
   if (u0 >= lo0 && u0 <= hi0 && u1 >= lo1 && u1 <= hi1) {
-    k0 = u0; k1 = u1; cl0 = false; cl1 = false;
+    r.k0 = u0; r.k1 = u1; r.cl0 = false; r.cl1 = false;
     return;
   }
   float best = INFINITY;
-  k0 = lo0 > 0.0f ? lo0 : (hi0 < 0.0f ? hi0 : 0.0f);
-  k1 = lo1 > 0.0f ? lo1 : (hi1 < 0.0f ? hi1 : 0.0f);
-  cl0 = true; cl1 = true;
+  r.k0 = lo0 > 0.0f ? lo0 : (hi0 < 0.0f ? hi0 : 0.0f);
+  r.k1 = lo1 > 0.0f ? lo1 : (hi1 < 0.0f ? hi1 : 0.0f);
+  r.cl0 = true; r.cl1 = true;
   // edges with u0 fixed (i = 0, j = 1), then u1 fixed (i = 1, j = 0); lo side before hi side
 #pragma unroll
   for (int side = 0; side < 2; ++side) {
@@ -131,7 +172,7 @@ __device__ __forceinline__ void box_qp2(float H00, float H01, float H11, float g
     const float ti = fmaf(0.5f * H00, b, g0);
     const float tj = fmaf(0.5f * H11, uj, g1);
     const float val = fmaf(ti, b, fmaf(tj, uj, (H01 * b) * uj));
-    if (val < best) { best = val; k0 = b; k1 = uj; cl0 = true; cl1 = cj; }
+    if (val < best) { best = val; r.k0 = b; r.k1 = uj; r.cl0 = true; r.cl1 = cj; }
   }
 #pragma unroll
   for (int side = 0; side < 2; ++side) {
@@ -143,16 +184,19 @@ __device__ __forceinline__ void box_qp2(float H00, float H01, float H11, float g
     const float ti = fmaf(0.5f * H11, b, g1);
     const float tj = fmaf(0.5f * H00, uj, g0);
     const float val = fmaf(ti, b, fmaf(tj, uj, (H01 * b) * uj));
-    if (val < best) { best = val; k1 = b; k0 = uj; cl1 = true; cl0 = cj; }
+    if (val < best) { best = val; r.k1 = b; r.k0 = uj; r.cl1 = true; r.cl0 = cj; }
   }
 }
 
 // ---- backward sweep -------------------------------------------------------------------------------
 // X [4T][n], U [2(T-1)][n] (field 2t+c, c = 0 delta, 1 a), xref [4T][n] (course frame; ox, oy are
 // subtracted on the fly), gains out G [14(T-1)][n].
-__device__ __forceinline__ void backward_sweep(int T, int64_t n, int64_t i, const float* X,
-                                               const float* U, const float* xref, float ox,
-                                               float oy, const MpcP& p, float* G) {
+__device__ __forceinline__ void backward_sweep(int T, int64_t n, int64_t i,
+                                               const float* __restrict__ X,
+                                               const float* __restrict__ U,
+                                               const float* __restrict__ xref, float ox,
+                                               float oy, const MpcP& p, bool gn,
+                                               float* __restrict__ G) {
   const int N = T - 1;
   const float R2[2] = {2.0f * p.w_delta, 2.0f * p.w_a};
   const float Rd2[2] = {2.0f * p.w_ddelta, 2.0f * p.w_da};
@@ -176,25 +220,34 @@ __device__ __forceinline__ void backward_sweep(int T, int64_t n, int64_t i, cons
       px[k] = Q2[k] * (X[((int64_t)N * 4 + k) * n + i] - xr);
     }
   }
-  float ut[2];  // U[t]
+  // Software pipeline: the operands of stage t-1 are requested at the top of stage t so that their
+  // L2/HBM latency hides under stage t's arithmetic (the sweep is a 19-long dependent chain).
+  float ut[2];                   // U[t]
+  float xt[4], xr[4], um[2];     // X[t], xref[t] (translated), U[t-1]
   ut[0] = U[((int64_t)(N - 1) * 2 + 0) * n + i];
   ut[1] = U[((int64_t)(N - 1) * 2 + 1) * n + i];
+  auto load_stage = [&](int t, float (&x_)[4], float (&r_)[4], float (&m_)[2]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) x_[k] = X[((int64_t)t * 4 + k) * n + i];
+    if (t >= 1) {
+      r_[0] = xref[((int64_t)t * 4 + 0) * n + i] - ox;
+      r_[1] = xref[((int64_t)t * 4 + 1) * n + i] - oy;
+      r_[2] = xref[((int64_t)t * 4 + 2) * n + i];
+      r_[3] = xref[((int64_t)t * 4 + 3) * n + i];
+      m_[0] = U[((int64_t)(t - 1) * 2 + 0) * n + i];
+      m_[1] = U[((int64_t)(t - 1) * 2 + 1) * n + i];
+    } else {
+      r_[0] = r_[1] = r_[2] = r_[3] = 0.0f;
+      m_[0] = m_[1] = 0.0f;
+    }
+  };
+  load_stage(N - 1, xt, xr, um);
 
   for (int t = N - 1; t >= 0; --t) {
     const bool hr = t >= 1;
-    float xt[4], xr[4], um[2] = {0.0f, 0.0f};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) xt[k] = X[((int64_t)t * 4 + k) * n + i];
-    if (hr) {
-      xr[0] = xref[((int64_t)t * 4 + 0) * n + i] - ox;
-      xr[1] = xref[((int64_t)t * 4 + 1) * n + i] - oy;
-      xr[2] = xref[((int64_t)t * 4 + 2) * n + i];
-      xr[3] = xref[((int64_t)t * 4 + 3) * n + i];
-      um[0] = U[((int64_t)(t - 1) * 2 + 0) * n + i];
-      um[1] = U[((int64_t)(t - 1) * 2 + 1) * n + i];
-    } else {
-      xr[0] = xr[1] = xr[2] = xr[3] = 0.0f;
-    }
+    float xt_n[4] = {0.0f, 0.0f, 0.0f, 0.0f}, xr_n[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    float um_n[2] = {0.0f, 0.0f};
+    if (t >= 1) load_stage(t - 1, xt_n, xr_n, um_n);
     const float v = xt[3];
     float s, c, sd, cd;
     crb_sincosf(xt[2], s, c);
@@ -228,8 +281,8 @@ __device__ __forceinline__ void backward_sweep(int T, int64_t n, int64_t i, cons
       qu[a] = g;
       qw[a] = hr ? -(Rd2[a] * du[a]) : 0.0f;
     }
-    const float hyy = -(vdt * fmaf(px[1], s, px[0] * c));
-    const float hyv = dt * fmaf(px[1], c, -(px[0] * s));
+    const float hyy = gn ? 0.0f : -(vdt * fmaf(px[1], s, px[0] * c));
+    const float hyv = gn ? 0.0f : dt * fmaf(px[1], c, -(px[0] * s));
 
     // G = Pxx A (structural zeros/ones of A skipped; same term order as the dense product)
     float Gm[4][4];
@@ -271,7 +324,7 @@ __device__ __forceinline__ void backward_sweep(int T, int64_t n, int64_t i, cons
       Qux[a][2] = bb * Gm[row][2] + W2;
       Qux[a][3] = bb * Gm[row][3] + W3;
     }
-    Qux[0][3] = fmaf(px[2], bv, Qux[0][3]);
+    if (!gn) Qux[0][3] = fmaf(px[2], bv, Qux[0][3]);
     // Quu = Luu + B^T Pxx B + B^T Pxw + Pwx B + Pww (+ second-order)
     const float PB20 = Pxx[2][2] * B20, PB21 = Pxx[2][3] * dt, PB31 = Pxx[3][3] * dt;
     const float BtPB00 = B20 * PB20, BtPB01 = B20 * PB21, BtPB11 = dt * PB31;
@@ -282,26 +335,23 @@ __device__ __forceinline__ void backward_sweep(int T, int64_t n, int64_t i, cons
     float Q00 = (((L0 + BtPB00) + BtPxw00) + BtPxw00) + Pww[0][0];
     const float Q01 = (((0.0f + BtPB01) + BtPxw01) + BtPxw10) + Pww[0][1];
     const float Q11 = (((L1 + BtPB11) + BtPxw11) + BtPxw11) + Pww[1][1];
-    Q00 = fmaf(px[2], (2.0f * tn) * B20, Q00);
+    if (!gn) Q00 = fmaf(px[2], (2.0f * tn) * B20, Q00);
     const float Quw[2] = {hr ? -Rd2[0] : 0.0f, hr ? -Rd2[1] : 0.0f};
     const float Qww[2] = {hr ? Rd2[0] : 0.0f, hr ? Rd2[1] : 0.0f};
-
-    // positive-definite shift for the gains
-    const float mh = 0.5f * (Q00 + Q11), dh = 0.5f * (Q00 - Q11);
-    const float lam = mh - sqrtf(fmaf(dh, dh, Q01 * Q01));
-    const float shift = lam < REG_EPS ? REG_EPS - lam : 0.0f;
-    const float H00 = Q00 + shift, H11 = Q11 + shift, H01 = Q01;
-    const float det = fmaf(H00, H11, -(H01 * H01));
-    const float idet = 1.0f / det, ih00 = 1.0f / H00, ih11 = 1.0f / H11;
 
     float alo, ahi;
     bool lo_sp, hi_sp;
     a_bounds(v, p, alo, ahi, lo_sp, hi_sp);
     const float lo0 = -p.max_steer - ut[0], lo1 = alo - ut[1];
     const float hi0 = p.max_steer - ut[0], hi1 = ahi - ut[1];
-    float k0, k1;
-    bool cl0, cl1;
-    box_qp2(H00, H01, H11, qu[0], qu[1], lo0, lo1, hi0, hi1, idet, ih00, ih11, k0, k1, cl0, cl1);
+    // Quu may be indefinite: projected-Newton box QP; gains from the regularised free-input Hessian,
+    // value update (below) with the true Quu
+    QpResult qp;
+    box_qp2(Q00, Q01, Q11, qu[0], qu[1], lo0, lo1, hi0, hi1, qp);
+    const float k0 = qp.k0, k1 = qp.k1;
+    const bool cl0 = qp.cl0, cl1 = qp.cl1;
+    const float H00 = qp.H00, H11 = qp.H11, H01 = Q01;
+    const float idet = qp.idet, ih00 = qp.ih00, ih11 = qp.ih11;
     float Kx[2][4], Kw[2][2];
 #pragma unroll
     for (int b = 0; b < 4; ++b) { Kx[0][b] = 0.0f; Kx[1][b] = 0.0f; }
@@ -418,14 +468,20 @@ __device__ __forceinline__ void backward_sweep(int T, int64_t n, int64_t i, cons
     Pww[0][0] = nPww[0][0]; Pww[0][1] = nPww[0][1]; Pww[1][0] = nPww[1][0]; Pww[1][1] = nPww[1][1];
     pw[0] = npw[0]; pw[1] = npw[1];
     ut[0] = um[0]; ut[1] = um[1];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { xt[k] = xt_n[k]; xr[k] = xr_n[k]; }
+    um[0] = um_n[0]; um[1] = um_n[1];
   }
 }
 
 // ---- forward sweep: clamped roll-out under the affine policy; returns dJ and sum|du| ----------------
 __device__ __forceinline__ void forward_sweep(int T, int64_t n, int64_t i, float yaw0, float v0,
-                                              const float* X, const float* U, const float* xref,
-                                              float ox, float oy, const float* G, float alpha,
-                                              const MpcP& p, float* Xn, float* Un, float& dJ_out,
+                                              const float* __restrict__ X,
+                                              const float* __restrict__ U,
+                                              const float* __restrict__ xref, float ox, float oy,
+                                              const float* __restrict__ G, float alpha,
+                                              const MpcP& p, float* __restrict__ Xn,
+                                              float* __restrict__ Un, float& dJ_out,
                                               float& du_out) {
   float dJ = 0.0f, dus = 0.0f;
   float xn[4] = {0.0f, 0.0f, yaw0, v0};   // Xn[t]
@@ -435,21 +491,29 @@ __device__ __forceinline__ void forward_sweep(int T, int64_t n, int64_t i, float
   for (int k = 0; k < 4; ++k) Xn[(int64_t)k * n + i] = xn[k];
   const float wu[2] = {p.w_delta, p.w_a};
   const float wd[2] = {p.w_ddelta, p.w_da};
-  for (int t = 0; t < T - 1; ++t) {
+  float uo[2], gk[NGAIN], xo1[4], xr1[4];
+  auto load_stage = [&](int t, float (&uo_)[2], float (&gk_)[NGAIN], float (&xo1_)[4],
+                        float (&xr1_)[4]) {
     const float* g = G + ((int64_t)t * NGAIN) * n + i;
-    float uo[2];
-    uo[0] = U[((int64_t)t * 2 + 0) * n + i];
-    uo[1] = U[((int64_t)t * 2 + 1) * n + i];
-    float gk[NGAIN];
+    uo_[0] = U[((int64_t)t * 2 + 0) * n + i];
+    uo_[1] = U[((int64_t)t * 2 + 1) * n + i];
 #pragma unroll
-    for (int j = 0; j < NGAIN; ++j) gk[j] = g[(int64_t)j * n];
-    float xo1[4], xr1[4];
+    for (int j = 0; j < NGAIN; ++j) gk_[j] = g[(int64_t)j * n];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) xo1[k] = X[((int64_t)(t + 1) * 4 + k) * n + i];
-    xr1[0] = xref[((int64_t)(t + 1) * 4 + 0) * n + i] - ox;
-    xr1[1] = xref[((int64_t)(t + 1) * 4 + 1) * n + i] - oy;
-    xr1[2] = xref[((int64_t)(t + 1) * 4 + 2) * n + i];
-    xr1[3] = xref[((int64_t)(t + 1) * 4 + 3) * n + i];
+    for (int k = 0; k < 4; ++k) xo1_[k] = X[((int64_t)(t + 1) * 4 + k) * n + i];
+    xr1_[0] = xref[((int64_t)(t + 1) * 4 + 0) * n + i] - ox;
+    xr1_[1] = xref[((int64_t)(t + 1) * 4 + 1) * n + i] - oy;
+    xr1_[2] = xref[((int64_t)(t + 1) * 4 + 2) * n + i];
+    xr1_[3] = xref[((int64_t)(t + 1) * 4 + 3) * n + i];
+  };
+  load_stage(0, uo, gk, xo1, xr1);
+  for (int t = 0; t < T - 1; ++t) {
+    // software pipeline: request stage t+1's operands before stage t's arithmetic
+    float uo_n[2] = {0.0f, 0.0f}, gk_n[NGAIN], xo1_n[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    float xr1_n[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int j = 0; j < NGAIN; ++j) gk_n[j] = 0.0f;
+    if (t + 1 < T - 1) load_stage(t + 1, uo_n, gk_n, xo1_n, xr1_n);
     float dx[4], dw[2] = {0.0f, 0.0f};
 #pragma unroll
     for (int k = 0; k < 4; ++k) dx[k] = xn[k] - xo[k];
@@ -497,6 +561,11 @@ __device__ __forceinline__ void forward_sweep(int T, int64_t n, int64_t i, float
 #pragma unroll
     for (int k = 0; k < 4; ++k) { xn[k] = xn1[k]; xo[k] = xo1[k]; }
     unm[0] = u[0]; unm[1] = u[1]; uom[0] = uo[0]; uom[1] = uo[1];
+    uo[0] = uo_n[0]; uo[1] = uo_n[1];
+#pragma unroll
+    for (int j = 0; j < NGAIN; ++j) gk[j] = gk_n[j];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { xo1[k] = xo1_n[k]; xr1[k] = xr1_n[k]; }
   }
   dJ_out = dJ;
   du_out = dus;
@@ -570,17 +639,25 @@ crb_mpc_solve_kernel(int64_t count, int64_t ld_in, int T, const float* __restric
   if (!(fabsf(J0) <= 3.0e38f)) {
     st = CRB_MPC_NONFINITE;
   } else {
-    for (int it = 0; it < p.max_iter; ++it) {
-      backward_sweep(T, n, i, X, U, xref, ox, oy, p, G);
+    bool gn = false;  // Newton sweep; Gauss-Newton retry after a failed line search
+    while (it_count < p.max_iter) {
+      backward_sweep(T, n, i, X, U, xref, ox, oy, p, gn, G);
       ++it_count;
-      bool accepted = false;
+      bool accepted = false, small = false;
       float dJ = 0.0f, du = 0.0f, alpha = 1.0f;
       for (int j = 0; j <= p.max_ls; ++j) {
         forward_sweep(T, n, i, yaw0, v0, X, U, xref, ox, oy, G, alpha, p, Xn, Un, dJ, du);
         if (dJ < 0.0f) { accepted = true; break; }
+        if (j == 0 && du <= p.du_th) { small = true; break; }  // full step below tolerance
         alpha = alpha * 0.5f;
       }
-      if (!accepted) { st = CRB_MPC_NO_DESCENT; break; }
+      if (small) { st = CRB_MPC_CONVERGED; break; }
+      if (!accepted) {
+        if (!gn) { gn = true; continue; }
+        st = CRB_MPC_NO_DESCENT;
+        break;
+      }
+      gn = false;
       float* tx = X; X = Xn; Xn = tx;
       float* tu = U; U = Un; Un = tu;
       if (du <= p.du_th) { st = CRB_MPC_CONVERGED; break; }

@@ -296,3 +296,48 @@ void crb_oracle_pf_estimate(int64_t n, const float* px, float* pw, float xEst[4]
   }
   for (int k = 0; k < 16; ++k) PEst[k] = (float)C[k];
 }
+
+/* ---- verification aids for the arithmetic shortcuts the CUDA PF kernel takes -------------------------
+ * (a) x / d for a launch-constant d computed without a divide: r = RN(1/d); q0 = x*r;
+ *     rem = fma(-q0, d, x); q = fma(rem, r, q0).  Returns how many floats x with bit patterns in
+ *     [lo_bits, hi_bits] give q != x / d (Markstein: none, barring under/overflow).
+ * (b) (float)(pre * (double)e) computed in binary32 as a float-float product.  Returns the number of
+ *     mismatches over the same range of e. */
+int64_t crb_oracle_check_const_division(float d, uint32_t lo_bits, uint32_t hi_bits) {
+  const float r = 1.0f / d;
+  int64_t bad = 0;
+#ifdef _OPENMP
+#pragma omp parallel for reduction(+ : bad) schedule(static)
+#endif
+  for (int64_t b = (int64_t)lo_bits; b <= (int64_t)hi_bits; ++b) {
+    uint32_t u = (uint32_t)b;
+    float x;
+    memcpy(&x, &u, 4);
+    const float q0 = x * r;
+    const float rem = fmaf(-q0, d, x);
+    const float q = fmaf(rem, r, q0);
+    const float ref = x / d;
+    if (!(q == ref) && !(q != q && ref != ref)) ++bad;
+  }
+  return bad;
+}
+int64_t crb_oracle_check_ff_product(double pre, uint32_t lo_bits, uint32_t hi_bits) {
+  const float ph_c = (float)pre;
+  const float pl_c = (float)(pre - (double)ph_c);
+  int64_t bad = 0;
+#ifdef _OPENMP
+#pragma omp parallel for reduction(+ : bad) schedule(static)
+#endif
+  for (int64_t b = (int64_t)lo_bits; b <= (int64_t)hi_bits; ++b) {
+    uint32_t u = (uint32_t)b;
+    float e;
+    memcpy(&e, &u, 4);
+    const float ph = ph_c * e;
+    const float err = fmaf(ph_c, e, -ph);
+    const float c = fmaf(pl_c, e, err);
+    const float p = ph + c;
+    const float ref = (float)(pre * (double)e);
+    if (!(p == ref)) ++bad;
+  }
+  return bad;
+}

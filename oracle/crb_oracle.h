@@ -58,6 +58,9 @@ void crb_oracle_pf_estimate(int64_t n, const float* px, float* pw, float xEst[4]
                             double* sum_w);
 
 int crb_oracle_num_threads(void);
+/* verification aids for arithmetic shortcuts of the CUDA PF kernel (see crb_oracle.c) */
+int64_t crb_oracle_check_const_division(float d, uint32_t lo_bits, uint32_t hi_bits);
+int64_t crb_oracle_check_ff_product(double pre, uint32_t lo_bits, uint32_t hi_bits);
 
 #ifdef __cplusplus
 }

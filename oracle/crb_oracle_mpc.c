@@ -18,13 +18,16 @@
  *     backward sweep t = T-2..0 along the current roll-out (X, U):
  *       linearise the dynamics (A_t, B_t and their second derivatives), build the quadratic model of
  *       the cost-to-go in (x_t, w_t = u_{t-1}, u_t)   [w carries the input-rate cost :207-210],
- *       shift Quu to be positive definite if it is not, solve the 2-D box QP in u_t exactly
+ *       projected-Newton step of the 2-D box QP in u_t (Quu may be indefinite: inputs pinned to a bound
+ *       by the gradient are fixed, the Hessian of the others is shifted to positive definite)
  *       (|delta| <= MAX_STEER, |a| <= MAX_ACCEL, MIN_SPEED <= v_{t+1} <= MAX_SPEED folded into the
  *       bound on a_t), feedback gains for the free inputs, Riccati update of the value function
  *     forward sweep with step alpha = 1, 1/2, ... : clamped non-linear roll-out under the affine
  *       policy; accept the first alpha that decreases the cost (difference accumulated term by term
  *       as (q'-q)(q'+q) so that it is accurate in binary32)
- *   until sum|dU| <= du_th  (or no alpha decreases the cost: already stationary)
+ *     (if no alpha decreases the cost, the sweep is redone once in Gauss-Newton mode, i.e. without the
+ *      second-derivative terms, which always yields a descent direction)
+ *   until sum|dU| <= du_th  (or neither mode decreases the cost: stationary to binary32 resolution)
  *
  * ARITHMETIC CONTRACT shared with the CUDA kernel: binary32 throughout; every a*b+c that is meant
  * to be fused is written fmaf(); nothing else may be contracted (gcc -ffp-contract=off, nvcc
@@ -44,8 +47,8 @@
 
 #include "crb_oracle_mpc.h"
 
-#define NX 4
-#define NU 2
+#include <stdio.h>
+int crb_oracle_mpc_trace = 0; /* debugging aid: print one line per outer iteration to stderr */
 
 /* ---- sin/cos: Cody-Waite reduction by pi/2 + Cephes-style minimax polynomials ------------------- */
 void crb_oracle_sincosf(float x, float* sn, float* cs) {
@@ -163,22 +166,70 @@ typedef struct {
 
 #define REG_EPS 1.0e-3f
 
-/* exact minimiser of 0.5 u'Hu + g'u over the box [lo, hi]^2; returns clamp flags */
-static void box_qp2(float H00, float H01, float H11, const float g[2], const float lo[2],
-                    const float hi[2], float idet, float ih00, float ih11, float k[2], int cl[2]) {
+typedef struct {
+  float k[2];      /* minimiser (du) */
+  int cl[2];       /* clamped flags */
+  float H00, H11;  /* regularised diagonal used for the gains (H01 is never changed) */
+  float idet, ih00, ih11;
+} qp_result;
+
+/* Projected-Newton step for min 0.5 u'Qu + g'u over the box [lo, hi]^2 (which contains 0); Q may be
+ * indefinite.  1. Inputs that sit on a bound with the gradient pushing outward are fixed first
+ * (Bertsekas' strongly active set).  2. The Hessian of the remaining inputs is made positive definite
+ * (1-D: max(Qjj, eps); 2-D: eigenvalue shift).  3. The convex box QP in those inputs is solved exactly:
+ * interior point if feasible, else the best of the four clamped edge minimisers (edge order u0 = lo0,
+ * hi0, u1 = lo1, hi1; strict '<' keeps the first). */
+static void box_qp2(float Q00, float Q01, float Q11, const float g[2], const float lo[2],
+                    const float hi[2], qp_result* r) {
+  const int sa0lo = lo[0] >= 0.0f && g[0] > 0.0f, sa0hi = !sa0lo && hi[0] <= 0.0f && g[0] < 0.0f;
+  const int sa1lo = lo[1] >= 0.0f && g[1] > 0.0f, sa1hi = !sa1lo && hi[1] <= 0.0f && g[1] < 0.0f;
+  const int sa0 = sa0lo || sa0hi, sa1 = sa1lo || sa1hi;
+  r->H00 = Q00; r->H11 = Q11; r->idet = 0.0f; r->ih00 = 0.0f; r->ih11 = 0.0f;
+  r->k[0] = 0.0f; r->k[1] = 0.0f;
+  if (sa0) r->k[0] = sa0lo ? lo[0] : hi[0];
+  if (sa1) r->k[1] = sa1lo ? lo[1] : hi[1];
+  if (sa0 && sa1) { r->cl[0] = 1; r->cl[1] = 1; return; }
+  if (sa0) { /* u1 free, 1-D */
+    r->H11 = Q11 > REG_EPS ? Q11 : REG_EPS;
+    r->ih11 = 1.0f / r->H11;
+    float uj = -(fmaf(Q01, r->k[0], g[1]) * r->ih11);
+    int cj = 0;
+    if (uj <= lo[1]) { uj = lo[1]; cj = 1; }
+    else if (uj >= hi[1]) { uj = hi[1]; cj = 1; }
+    r->k[1] = uj; r->cl[0] = 1; r->cl[1] = cj;
+    return;
+  }
+  if (sa1) { /* u0 free, 1-D */
+    r->H00 = Q00 > REG_EPS ? Q00 : REG_EPS;
+    r->ih00 = 1.0f / r->H00;
+    float uj = -(fmaf(Q01, r->k[1], g[0]) * r->ih00);
+    int cj = 0;
+    if (uj <= lo[0]) { uj = lo[0]; cj = 1; }
+    else if (uj >= hi[0]) { uj = hi[0]; cj = 1; }
+    r->k[0] = uj; r->cl[1] = 1; r->cl[0] = cj;
+    return;
+  }
+  /* both free: shift to positive definite, then the convex 2-D box QP */
+  const float mh = 0.5f * (Q00 + Q11), dh = 0.5f * (Q00 - Q11);
+  const float lam = mh - sqrtf(fmaf(dh, dh, Q01 * Q01));
+  const float shift = lam < REG_EPS ? REG_EPS - lam : 0.0f;
+  const float H00 = Q00 + shift, H11 = Q11 + shift, H01 = Q01;
+  const float det = fmaf(H00, H11, -(H01 * H01));
+  const float idet = 1.0f / det, ih00 = 1.0f / H00, ih11 = 1.0f / H11;
+  r->H00 = H00; r->H11 = H11; r->idet = idet; r->ih00 = ih00; r->ih11 = ih11;
   const float n0 = fmaf(H01, g[1], -(H11 * g[0]));
   const float n1 = fmaf(H01, g[0], -(H00 * g[1]));
   const float u0 = n0 * idet, u1 = n1 * idet;
   if (u0 >= lo[0] && u0 <= hi[0] && u1 >= lo[1] && u1 <= hi[1]) {
-    k[0] = u0; k[1] = u1; cl[0] = 0; cl[1] = 0;
+    r->k[0] = u0; r->k[1] = u1; r->cl[0] = 0; r->cl[1] = 0;
     return;
   }
   const float Hd[2] = {H00, H11};
   const float ih[2] = {ih00, ih11};
   float best = INFINITY;
-  k[0] = lo[0] > 0.0f ? lo[0] : (hi[0] < 0.0f ? hi[0] : 0.0f); /* only reached if every edge is NaN */
-  k[1] = lo[1] > 0.0f ? lo[1] : (hi[1] < 0.0f ? hi[1] : 0.0f);
-  cl[0] = 1; cl[1] = 1;
+  r->k[0] = lo[0] > 0.0f ? lo[0] : (hi[0] < 0.0f ? hi[0] : 0.0f); /* only kept if every edge is NaN */
+  r->k[1] = lo[1] > 0.0f ? lo[1] : (hi[1] < 0.0f ? hi[1] : 0.0f);
+  r->cl[0] = 1; r->cl[1] = 1;
   for (int i = 0; i < 2; ++i) {
     const int j = 1 - i;
     for (int side = 0; side < 2; ++side) {
@@ -192,14 +243,14 @@ static void box_qp2(float H00, float H01, float H11, const float g[2], const flo
       const float val = fmaf(ti, b, fmaf(tj, uj, (H01 * b) * uj));
       if (val < best) {
         best = val;
-        k[i] = b; k[j] = uj; cl[i] = 1; cl[j] = cj;
+        r->k[i] = b; r->k[j] = uj; r->cl[i] = 1; r->cl[j] = cj;
       }
     }
   }
 }
 
 static void backward_sweep(int T, const float X[][4], const float U[][2], const float xref[][4],
-                           const crb_oracle_mpc_params* p, stage_gain* gains) {
+                           const crb_oracle_mpc_params* p, int gn, stage_gain* gains) {
   const int N = T - 1;
   const float R2[2] = {2.0f * p->w_delta, 2.0f * p->w_a};
   const float Rd2[2] = {2.0f * p->w_ddelta, 2.0f * p->w_da};
@@ -251,8 +302,9 @@ static void backward_sweep(int T, const float X[][4], const float U[][2], const 
       qw[i] = hr ? -(Rd2[i] * du[i]) : 0.0f;
     }
     /* second derivatives of the dynamics contracted with the costate px (p0,p1,p2) */
-    const float hyy = -(vdt * fmaf(px[1], s, px[0] * c));
-    const float hyv = dt * fmaf(px[1], c, -(px[0] * s));
+    /* (skipped in Gauss-Newton mode, gn) */
+    const float hyy = gn ? 0.0f : -(vdt * fmaf(px[1], s, px[0] * c));
+    const float hyv = gn ? 0.0f : dt * fmaf(px[1], c, -(px[0] * s));
     /* Hessian blocks */
     float G[16], Qxx[16];
     mm(Pxx, A, G, 4, 4, 4);
@@ -268,7 +320,7 @@ static void backward_sweep(int T, const float X[][4], const float U[][2], const 
     mm(Pwx, A, W, 2, 4, 4);
     mtm(B, G, BtG, 2, 4, 4);
     for (int i = 0; i < 8; ++i) Qux[i] = BtG[i] + W[i];
-    Qux[0 * 4 + 3] = fmaf(px[2], bv, Qux[0 * 4 + 3]);
+    if (!gn) Qux[0 * 4 + 3] = fmaf(px[2], bv, Qux[0 * 4 + 3]);
     float PB[8], BtPB[4], BtPxw[4];
     mm(Pxx, B, PB, 4, 4, 2);
     mtm(B, PB, BtPB, 2, 4, 2);
@@ -278,17 +330,9 @@ static void backward_sweep(int T, const float X[][4], const float U[][2], const 
     float Q00 = (((L0 + BtPB[0]) + BtPxw[0]) + BtPxw[0]) + Pww[0];
     float Q01 = (((0.0f + BtPB[1]) + BtPxw[1]) + BtPxw[2]) + Pww[1];
     float Q11 = (((L1 + BtPB[3]) + BtPxw[3]) + BtPxw[3]) + Pww[3];
-    Q00 = fmaf(px[2], (2.0f * tn) * B20, Q00);
+    if (!gn) Q00 = fmaf(px[2], (2.0f * tn) * B20, Q00);
     const float Quw[2] = {hr ? -Rd2[0] : 0.0f, hr ? -Rd2[1] : 0.0f}; /* diagonal */
     const float Qww[2] = {hr ? Rd2[0] : 0.0f, hr ? Rd2[1] : 0.0f};   /* diagonal */
-
-    /* shift Quu to positive definite when needed (gains only; the value update uses the true Quu) */
-    const float mh = 0.5f * (Q00 + Q11), dh = 0.5f * (Q00 - Q11);
-    const float lam = mh - sqrtf(fmaf(dh, dh, Q01 * Q01));
-    const float shift = lam < REG_EPS ? REG_EPS - lam : 0.0f;
-    const float H00 = Q00 + shift, H11 = Q11 + shift, H01 = Q01;
-    const float det = fmaf(H00, H11, -(H01 * H01));
-    const float idet = 1.0f / det, ih00 = 1.0f / H00, ih11 = 1.0f / H11;
 
     /* box on du = u - ubar */
     float alo, ahi;
@@ -296,88 +340,94 @@ static void backward_sweep(int T, const float X[][4], const float U[][2], const 
     a_bounds(v, p, &alo, &ahi, &lo_sp, &hi_sp);
     const float lo[2] = {-p->max_steer - U[t][0], alo - U[t][1]};
     const float hi[2] = {p->max_steer - U[t][0], ahi - U[t][1]};
-    stage_gain* gn = &gains[t];
-    int cl[2];
-    box_qp2(H00, H01, H11, qu, lo, hi, idet, ih00, ih11, gn->k, cl);
-    memset(gn->Kx, 0, sizeof(gn->Kx));
-    memset(gn->Kw, 0, sizeof(gn->Kw));
+    stage_gain* gn_ = &gains[t];
+    /* Quu may be indefinite (exact second derivatives): projected-Newton box QP; the gains use the
+     * regularised Hessian of the free inputs, the value update below uses the true Quu */
+    qp_result qp;
+    box_qp2(Q00, Q01, Q11, qu, lo, hi, &qp);
+    const int cl[2] = {qp.cl[0], qp.cl[1]};
+    gn_->k[0] = qp.k[0]; gn_->k[1] = qp.k[1];
+    const float H00 = qp.H00, H11 = qp.H11, H01 = Q01;
+    const float idet = qp.idet, ih00 = qp.ih00, ih11 = qp.ih11;
+    memset(gn_->Kx, 0, sizeof(gn_->Kx));
+    memset(gn_->Kw, 0, sizeof(gn_->Kw));
     if (cl[1]) { /* a speed-induced bound on a moves with v: da/dv = -1/dt */
-      const int at_lo = gn->k[1] <= lo[1];
-      if ((at_lo && lo_sp) || (!at_lo && hi_sp)) gn->Kx[1][3] = -inv_dt;
+      const int at_lo = gn_->k[1] <= lo[1];
+      if ((at_lo && lo_sp) || (!at_lo && hi_sp)) gn_->Kx[1][3] = -inv_dt;
     }
     if (!cl[0] && !cl[1]) {
       for (int j = 0; j < 4; ++j) {
-        gn->Kx[0][j] = fmaf(H01, Qux[1 * 4 + j], -(H11 * Qux[0 * 4 + j])) * idet;
-        gn->Kx[1][j] = fmaf(H01, Qux[0 * 4 + j], -(H00 * Qux[1 * 4 + j])) * idet;
+        gn_->Kx[0][j] = fmaf(H01, Qux[1 * 4 + j], -(H11 * Qux[0 * 4 + j])) * idet;
+        gn_->Kx[1][j] = fmaf(H01, Qux[0 * 4 + j], -(H00 * Qux[1 * 4 + j])) * idet;
       }
       /* Quw is diagonal: column 0 = (Quw0, 0), column 1 = (0, Quw1) */
-      gn->Kw[0][0] = fmaf(H01, 0.0f, -(H11 * Quw[0])) * idet;
-      gn->Kw[1][0] = fmaf(H01, Quw[0], -(H00 * 0.0f)) * idet;
-      gn->Kw[0][1] = fmaf(H01, Quw[1], -(H11 * 0.0f)) * idet;
-      gn->Kw[1][1] = fmaf(H01, 0.0f, -(H00 * Quw[1])) * idet;
+      gn_->Kw[0][0] = fmaf(H01, 0.0f, -(H11 * Quw[0])) * idet;
+      gn_->Kw[1][0] = fmaf(H01, Quw[0], -(H00 * 0.0f)) * idet;
+      gn_->Kw[0][1] = fmaf(H01, Quw[1], -(H11 * 0.0f)) * idet;
+      gn_->Kw[1][1] = fmaf(H01, 0.0f, -(H00 * Quw[1])) * idet;
     } else if (!cl[0] || !cl[1]) {
       const int j = cl[0] ? 1 : 0, i = 1 - j;
       const float ihjj = j ? ih11 : ih00;
       for (int col = 0; col < 4; ++col)
-        gn->Kx[j][col] = -(fmaf(H01, gn->Kx[i][col], Qux[j * 4 + col]) * ihjj);
+        gn_->Kx[j][col] = -(fmaf(H01, gn_->Kx[i][col], Qux[j * 4 + col]) * ihjj);
       for (int col = 0; col < 2; ++col) {
         const float quw_jc = (col == j) ? Quw[j] : 0.0f;
-        gn->Kw[j][col] = -(fmaf(H01, gn->Kw[i][col], quw_jc) * ihjj);
+        gn_->Kw[j][col] = -(fmaf(H01, gn_->Kw[i][col], quw_jc) * ihjj);
       }
     }
     /* value-function update for the affine policy du = k + Kx dx + Kw dw, with the TRUE Quu */
-    const float k0 = gn->k[0], k1 = gn->k[1];
+    const float k0 = gn_->k[0], k1 = gn_->k[1];
     const float m0 = fmaf(Q01, k1, fmaf(Q00, k0, qu[0]));
     const float m1 = fmaf(Q11, k1, fmaf(Q01, k0, qu[1]));
     float Mx[2][4], Mw[2][2];
     for (int j = 0; j < 4; ++j) {
-      Mx[0][j] = fmaf(Q01, gn->Kx[1][j], fmaf(Q00, gn->Kx[0][j], Qux[0 * 4 + j]));
-      Mx[1][j] = fmaf(Q11, gn->Kx[1][j], fmaf(Q01, gn->Kx[0][j], Qux[1 * 4 + j]));
+      Mx[0][j] = fmaf(Q01, gn_->Kx[1][j], fmaf(Q00, gn_->Kx[0][j], Qux[0 * 4 + j]));
+      Mx[1][j] = fmaf(Q11, gn_->Kx[1][j], fmaf(Q01, gn_->Kx[0][j], Qux[1 * 4 + j]));
     }
     for (int b = 0; b < 2; ++b) {
-      Mw[0][b] = fmaf(Q01, gn->Kw[1][b], fmaf(Q00, gn->Kw[0][b], b == 0 ? Quw[0] : 0.0f));
-      Mw[1][b] = fmaf(Q11, gn->Kw[1][b], fmaf(Q01, gn->Kw[0][b], b == 1 ? Quw[1] : 0.0f));
+      Mw[0][b] = fmaf(Q01, gn_->Kw[1][b], fmaf(Q00, gn_->Kw[0][b], b == 0 ? Quw[0] : 0.0f));
+      Mw[1][b] = fmaf(Q11, gn_->Kw[1][b], fmaf(Q01, gn_->Kw[0][b], b == 1 ? Quw[1] : 0.0f));
     }
     float npx[4], npw[2], nPxx[16], nPxw[8], nPww[4];
     for (int i = 0; i < 4; ++i) {
       float acc = qx[i];
-      acc = fmaf(gn->Kx[0][i], m0, acc);
-      acc = fmaf(gn->Kx[1][i], m1, acc);
+      acc = fmaf(gn_->Kx[0][i], m0, acc);
+      acc = fmaf(gn_->Kx[1][i], m1, acc);
       acc = fmaf(Qux[0 * 4 + i], k0, acc);
       acc = fmaf(Qux[1 * 4 + i], k1, acc);
       npx[i] = acc;
     }
     for (int b = 0; b < 2; ++b) {
       float acc = qw[b];
-      acc = fmaf(gn->Kw[0][b], m0, acc);
-      acc = fmaf(gn->Kw[1][b], m1, acc);
+      acc = fmaf(gn_->Kw[0][b], m0, acc);
+      acc = fmaf(gn_->Kw[1][b], m1, acc);
       acc = fmaf(Quw[b], b == 0 ? k0 : k1, acc);
       npw[b] = acc;
     }
     for (int i = 0; i < 4; ++i)
       for (int j = 0; j <= i; ++j) {
         float acc = Qxx[i * 4 + j];
-        acc = fmaf(gn->Kx[0][i], Mx[0][j], acc);
-        acc = fmaf(gn->Kx[1][i], Mx[1][j], acc);
-        acc = fmaf(Qux[0 * 4 + i], gn->Kx[0][j], acc);
-        acc = fmaf(Qux[1 * 4 + i], gn->Kx[1][j], acc);
+        acc = fmaf(gn_->Kx[0][i], Mx[0][j], acc);
+        acc = fmaf(gn_->Kx[1][i], Mx[1][j], acc);
+        acc = fmaf(Qux[0 * 4 + i], gn_->Kx[0][j], acc);
+        acc = fmaf(Qux[1 * 4 + i], gn_->Kx[1][j], acc);
         nPxx[i * 4 + j] = acc;
         nPxx[j * 4 + i] = acc;
       }
     for (int i = 0; i < 4; ++i)
       for (int b = 0; b < 2; ++b) {
-        float acc = gn->Kx[0][i] * Mw[0][b];
-        acc = fmaf(gn->Kx[1][i], Mw[1][b], acc);
-        acc = fmaf(Qux[0 * 4 + i], gn->Kw[0][b], acc);
-        acc = fmaf(Qux[1 * 4 + i], gn->Kw[1][b], acc);
+        float acc = gn_->Kx[0][i] * Mw[0][b];
+        acc = fmaf(gn_->Kx[1][i], Mw[1][b], acc);
+        acc = fmaf(Qux[0 * 4 + i], gn_->Kw[0][b], acc);
+        acc = fmaf(Qux[1 * 4 + i], gn_->Kw[1][b], acc);
         nPxw[i * 2 + b] = acc;
       }
     for (int a = 0; a < 2; ++a)
       for (int b = 0; b <= a; ++b) {
         float acc = a == b ? Qww[a] : 0.0f;
-        acc = fmaf(gn->Kw[0][a], Mw[0][b], acc);
-        acc = fmaf(gn->Kw[1][a], Mw[1][b], acc);
-        acc = fmaf(Quw[a], gn->Kw[a][b], acc); /* sum_c Quw[c][a] Kw[c][b], Quw diagonal */
+        acc = fmaf(gn_->Kw[0][a], Mw[0][b], acc);
+        acc = fmaf(gn_->Kw[1][a], Mw[1][b], acc);
+        acc = fmaf(Quw[a], gn_->Kw[a][b], acc); /* sum_c Quw[c][a] Kw[c][b], Quw diagonal */
         nPww[a * 2 + b] = acc;
         nPww[b * 2 + a] = acc;
       }
@@ -479,18 +529,30 @@ void crb_oracle_mpc_solve(int T, const float x0_in[4], const float* xref_flat /*
   if (!(fabsf(J0) <= 3.0e38f)) {
     status = CRB_ORACLE_MPC_NONFINITE;
   } else {
-    for (int it = 0; it < p->max_iter; ++it) {
-      backward_sweep(T, (const float(*)[4])X, (const float(*)[2])U, (const float(*)[4])xref, p, gains);
+    int gn = 0; /* 0: Newton (exact second derivatives); 1: Gauss-Newton retry after a failed search */
+    while (iters < p->max_iter) {
+      backward_sweep(T, (const float(*)[4])X, (const float(*)[2])U, (const float(*)[4])xref, p, gn,
+                     gains);
       ++iters;
-      int accepted = 0;
+      int accepted = 0, small = 0;
       float dJ = 0.0f, du = 0.0f, alpha = 1.0f;
       for (int j = 0; j <= p->max_ls; ++j) {
         forward_sweep(T, x0, (const float(*)[4])X, (const float(*)[2])U, (const float(*)[4])xref,
                       gains, alpha, p, Xn, Un, &dJ, &du);
         if (dJ < 0.0f) { accepted = 1; break; }
+        if (j == 0 && du <= p->du_th) { small = 1; break; } /* full step below tolerance: converged */
         alpha = alpha * 0.5f;
       }
-      if (!accepted) { status = CRB_ORACLE_MPC_NO_DESCENT; break; }
+      if (crb_oracle_mpc_trace)
+        fprintf(stderr, "  it %d gn %d accepted %d alpha %g dJ %.3e du %.3e\n", iters, gn, accepted,
+                (double)alpha, (double)dJ, (double)du);
+      if (small) { status = CRB_ORACLE_MPC_CONVERGED; break; }
+      if (!accepted) {
+        if (!gn) { gn = 1; continue; }
+        status = CRB_ORACLE_MPC_NO_DESCENT;
+        break;
+      }
+      gn = 0;
       float(*tx)[4] = X; X = Xn; Xn = tx;
       float(*tu)[2] = U; U = Un; Un = tu;
       if (du <= p->du_th) { status = CRB_ORACLE_MPC_CONVERGED; break; }

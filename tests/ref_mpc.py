@@ -73,15 +73,43 @@ def rollout(x0, U, p):
 
 
 def box_qp2(H, g, lo, hi):
-    """Exact minimiser of 0.5 u'Hu + g'u on a 2-D box; returns (u, clamped[2])."""
-    u = -np.linalg.solve(H, g)
+    """Projected-Newton step for min 0.5 u'Hu + g'u on a 2-D box that contains 0 (H may be indefinite).
+    Inputs that sit on a bound with the gradient pushing outward are fixed first (Bertsekas' strongly
+    active set); the Hessian of the remaining inputs is shifted to be positive definite, and the convex
+    box QP in those inputs is solved exactly.  Returns (u, clamped[2], H_reg)."""
+    sa = np.zeros(2, bool)
+    u = np.zeros(2)
+    for i in (0, 1):
+        if lo[i] >= 0.0 and g[i] > 0.0:
+            sa[i], u[i] = True, lo[i]
+        elif hi[i] <= 0.0 and g[i] < 0.0:
+            sa[i], u[i] = True, hi[i]
+    Hr = H.copy()
+    if sa.all():
+        return u, np.array([True, True]), Hr
+    if sa.any():
+        i = int(np.argmax(sa)); j = 1 - i
+        Hr[j, j] = max(H[j, j], REG_EPS)
+        uj = -(g[j] + H[j, i] * u[i]) / Hr[j, j]
+        cj = False
+        if uj <= lo[j]:
+            uj, cj = lo[j], True
+        elif uj >= hi[j]:
+            uj, cj = hi[j], True
+        u[j] = uj
+        cl = np.array([True, True]); cl[j] = cj
+        return u, cl, Hr
+    lam = np.linalg.eigvalsh(H)[0]
+    if lam < REG_EPS:
+        Hr = H + (REG_EPS - lam) * np.eye(2)
+    u = -np.linalg.solve(Hr, g)
     if np.all(u >= lo) and np.all(u <= hi):
-        return u, np.array([False, False])
+        return u, np.array([False, False]), Hr
     best, bu, bc = np.inf, None, None
     for i in (0, 1):
         j = 1 - i
         for b in (lo[i], hi[i]):
-            uj = -(g[j] + H[j, i] * b) / H[j, j]
+            uj = -(g[j] + Hr[j, i] * b) / Hr[j, j]
             cj = False
             if uj <= lo[j]:
                 uj, cj = lo[j], True
@@ -89,15 +117,15 @@ def box_qp2(H, g, lo, hi):
                 uj, cj = hi[j], True
             cand = np.zeros(2)
             cand[i], cand[j] = b, uj
-            val = 0.5 * cand @ H @ cand + g @ cand
+            val = 0.5 * cand @ Hr @ cand + g @ cand
             if val < best:
                 cl = np.zeros(2, bool)
                 cl[i], cl[j] = True, cj
                 best, bu, bc = val, cand, cl
-    return bu, bc
+    return bu, bc, Hr
 
 
-def backward(X, U, xref, p):
+def backward(X, U, xref, p, gauss_newton=False):
     """Riccati recursion on z = (x, w) with w = previous input.  Returns k [2,N], K [2,6,N], dV1, dV2."""
     N = U.shape[1]
     dt, wb = p["dt"], p["wb"]
@@ -139,21 +167,17 @@ def backward(X, U, xref, p):
         Quz = Luz + Bz.T @ P @ Az
         Quu = Luu + Bz.T @ P @ Bz
         # second derivatives of the dynamics (:242-245) contracted with the costate of x_{t+1}
-        p0, p1, p2 = pv[0], pv[1], pv[2]
-        Qzz[2, 2] += p0 * (-v * np.cos(yaw) * dt) + p1 * (-v * np.sin(yaw) * dt)
-        Qzz[2, 3] += p0 * (-np.sin(yaw) * dt) + p1 * (np.cos(yaw) * dt)
-        Qzz[3, 2] += p0 * (-np.sin(yaw) * dt) + p1 * (np.cos(yaw) * dt)
-        Quz[0, 3] += p2 * dt / (wb * np.cos(d) ** 2)
-        Quu[0, 0] += p2 * v * dt * 2.0 * np.tan(d) / (wb * np.cos(d) ** 2)
-        # gains from a positive-definite shifted copy; the value update keeps the true Quu
-        Quu_true = Quu
-        lam = np.linalg.eigvalsh(Quu)[0]
-        if lam < REG_EPS:
-            Quu = Quu + (REG_EPS - lam) * np.eye(2)
+        if not gauss_newton:
+            p0, p1, p2 = pv[0], pv[1], pv[2]
+            Qzz[2, 2] += p0 * (-v * np.cos(yaw) * dt) + p1 * (-v * np.sin(yaw) * dt)
+            Qzz[2, 3] += p0 * (-np.sin(yaw) * dt) + p1 * (np.cos(yaw) * dt)
+            Qzz[3, 2] += p0 * (-np.sin(yaw) * dt) + p1 * (np.cos(yaw) * dt)
+            Quz[0, 3] += p2 * dt / (wb * np.cos(d) ** 2)
+            Quu[0, 0] += p2 * v * dt * 2.0 * np.tan(d) / (wb * np.cos(d) ** 2)
         lo_a, hi_a, lo_sp, hi_sp = a_bounds(v, p)
         lo = np.array([-p["max_steer"], lo_a]) - U[:, t]
         hi = np.array([p["max_steer"], hi_a]) - U[:, t]
-        k, cl = box_qp2(Quu, qu, lo, hi)
+        k, cl, Hr = box_qp2(Quu, qu, lo, hi)
         K = np.zeros((2, 6))
         # a speed-induced bound on a moves with v: a = (bound - v)/dt  =>  da/dv = -1/dt
         if cl[1]:
@@ -162,15 +186,15 @@ def backward(X, U, xref, p):
                 K[1, 3] = -1.0 / dt
         fr = ~cl
         if fr.all():
-            K = -np.linalg.solve(Quu, Quz)
+            K = -np.linalg.solve(Hr, Quz)
         elif fr.any():
             j = int(np.argmax(fr)); i = 1 - j
-            K[j] = -(Quz[j] + Quu[j, i] * K[i]) / Quu[j, j]
+            K[j] = -(Quz[j] + Hr[j, i] * K[i]) / Hr[j, j]
         ks[:, t] = k; Ks[:, :, t] = K
         dV1 += k @ qu
         dV2 += 0.5 * k @ Quu @ k
-        pv = qz + K.T @ Quu_true @ k + K.T @ qu + Quz.T @ k
-        P = Qzz + K.T @ Quu_true @ K + K.T @ Quz + Quz.T @ K
+        pv = qz + K.T @ Quu @ k + K.T @ qu + Quz.T @ k
+        P = Qzz + K.T @ Quu @ K + K.T @ Quz + Quz.T @ K
         P = 0.5 * (P + P.T)
     return ks, Ks, dV1, dV2
 
@@ -201,19 +225,31 @@ def box_ilqr(x0, xref, p=None, U_init=None):
     X, U = rollout(np.asarray(x0, float), U, p)
     J = nlp_cost(X, U, xref, p)
     status, iters = 1, 0
-    for _ in range(p["max_iter"]):
-        ks, Ks, dV1, dV2 = backward(X, U, xref, p)
+    gn = False
+    while iters < p["max_iter"]:
+        ks, Ks, dV1, dV2 = backward(X, U, xref, p, gauss_newton=gn)
         iters += 1
         accepted = False
+        small = False
         for j in range(p["max_ls"] + 1):
             Xn, Un = forward(x0, X, U, ks, Ks, 0.5 ** j, p)
             Jn = nlp_cost(Xn, Un, xref, p)
             if Jn < J:
                 accepted = True
                 break
+            if j == 0 and np.abs(Un - U).sum() <= p["du_th"]:
+                small = True      # the full step is already below the tolerance: converged
+                break
+        if small:
+            status = 0
+            break
         if not accepted:
+            if not gn:          # Newton step found no descent: retry this iterate with Gauss-Newton
+                gn = True
+                continue
             status = 2
             break
+        gn = False
         du = np.abs(Un - U).sum()
         X, U, J = Xn, Un, Jn
         if du <= p["du_th"]:
