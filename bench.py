@@ -170,21 +170,50 @@ def pinned(a):
 # =========================================================================================================
 # workloads: each returns a dict with value / ms_per_step / roofline / e2e / cpu_baseline pieces
 # =========================================================================================================
-def time_device_steps(step_fn, steps, warmup, world, after_fn=None):
-    """W untimed + K timed steps between barrier+sync brackets; CUDA events on the current stream."""
+def time_device_steps(step_fn, steps, warmup, world, after_fn=None, eng=None, graph=True):
+    """W untimed + K timed steps between barrier+sync brackets; CUDA events on the launching stream.
+    The K steps (+ the optional tail) are captured once into a CUDA graph and the timed region is one
+    replay of it, so that host-side launch overhead (Python/ctypes) is not what is measured; if capture
+    is not possible the steps are enqueued directly.  Returns (ms, mode)."""
     import torch
     for k in range(warmup):
         step_fn(k)
+    if after_fn is not None:
+        after_fn()
+    mode = "stream"
+    g = None
+    if graph and eng is not None:
+        try:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                eng.bind_current_stream()
+                for k in range(steps):
+                    step_fn(warmup + k)
+                if after_fn is not None and world == 1:
+                    after_fn()
+            eng.bind_current_stream()
+            g.replay()                      # one untimed replay
+            mode = "cuda_graph"
+        except Exception as exc:            # pragma: no cover - depends on driver / torch
+            sys.stderr.write(f"graph capture failed ({exc}); timing direct launches\n")
+            eng.bind_current_stream()
+            g = None
     barrier_sync(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for k in range(steps):
-        step_fn(warmup + k)
-    if after_fn is not None:
-        after_fn()
+    if g is not None:
+        g.replay()
+        if after_fn is not None and world > 1:
+            after_fn()                      # the NCCL all-gather stays outside the graph
+    else:
+        for k in range(steps):
+            step_fn(warmup + k)
+        if after_fn is not None:
+            after_fn()
     e1.record()
     barrier_sync(world)
-    return max_over_ranks(e0.elapsed_time(e1), world)
+    return max_over_ranks(e0.elapsed_time(e1), world), mode
 
 
 def time_host_steps(step_fn, steps, warmup, world):
@@ -237,15 +266,13 @@ def bench_ekf(eng, rank, world, steps, warmup, with_cpu):
         eng.stats_reduce(sets[0][0][0], i0=rank * n, out=stats)   # summary of the x field
         gather_stats(stats, world)
 
-    for k in range(warmup):
-        step(k)
     l0 = eng.launches
-    ms = time_device_steps(step, steps, 0, world, after)
-    launches = eng.launches - l0
+    ms, mode = time_device_steps(step, steps, warmup, world, after, eng=eng)
+    launches = steps + 2                     # K filter kernels + the two stats-reduction kernels
     value = world * n * steps / (ms * 1e-3)
     # roofline of the dominant kernel (one launch per step): algorithmic bytes / avg launch duration.
     # measured separately WITHOUT the stats tail so that it is the kernel alone.
-    ms_k = time_device_steps(step, steps, 3, world)
+    ms_k, _ = time_device_steps(step, steps, 3, world, eng=eng)
     peak, peak_src, _ = peaks()
     achieved = EKF_BYTES * n * steps / (ms_k * 1e-3) / 1e9
     # e2e through the host-pointer C-ABI entry: pinned host buffers, H2D + kernel + D2H every step
@@ -253,7 +280,7 @@ def bench_ekf(eng, rank, world, steps, warmup, with_cpu):
     ms_e = time_host_steps(lambda k: eng.ekf_estimation_host(hx, hP, hz, hu), max(3, min(steps, 10)),
                            warmup, world)
     e_steps = max(3, min(steps, 10))
-    out = dict(value=value, ms=ms / steps, launches=launches,
+    out = dict(value=value, ms=ms / steps, launches=launches, launch_mode=mode,
                roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s",
                              frac=achieved / peak, traffic=traffic_for("ekf"), peak_source=peak_src,
                              kernel="crb_ekf_step_kernel",
@@ -297,7 +324,7 @@ def bench_pf(eng, rank, world, steps, warmup, with_cpu):
         px, pw, noise = sets[k % len(sets)]
         eng.pf_predict_weight(px, pw, noise, lm)
 
-    ms_k = time_device_steps(step_nofill, steps, warmup, world)
+    ms_k, _ = time_device_steps(step_nofill, steps, warmup, world, eng=eng)
     value = world * n * steps / (ms_k * 1e-3)
     peak, peak_src, _ = peaks()
     achieved = PF_BYTES * n * steps / (ms_k * 1e-3) / 1e9
@@ -375,9 +402,9 @@ def bench_mpc(eng, rank, world, steps, warmup, with_cpu):
         s, xr = sets[k % NSETS]
         eng.mpc_solve(s, xr, T, prm, sol=sol, u0=u0, cost=cost, status=status, iters=iters)
 
-    ms = time_device_steps(step, steps, warmup, world)
+    ms, _ = time_device_steps(step, steps, warmup, world, graph=False)   # NCCL gather every step
     value = world * n * steps / (ms * 1e-3)
-    ms_k = time_device_steps(step_kernel_only, steps, 1, world)
+    ms_k, _ = time_device_steps(step_kernel_only, steps, 1, world, eng=eng)
     g = gathered["g"].cpu().numpy()
     iters_sum = float(g[:, 5].sum())
     # governing roofline: the solver's working set (trajectories + gains, 502 floats/problem) streams
@@ -472,7 +499,8 @@ def run_ours(args):
         "config": {"workload": "ekf_2^20_agents_1_step_per_gpu (BASELINE.json configs[1])",
                    "agents_per_gpu": EKF_N, "global_agents": EKF_N * world,
                    "l2": "3 rotating buffer sets, 303 MB of inputs > 126 MB L2",
-                   "collective": "one all-gather of 8 doubles per rank inside the timed region"},
+                   "collective": "one all-gather of 8 doubles per rank inside the timed region",
+                   "launch": head["launch_mode"]},
         "clocks": clk.summary(), "e2e": head["e2e"], "gpu_launches": head["launches"],
         "roofline": head["roofline"],
     }

@@ -38,7 +38,7 @@ class MpcParams(C.Structure):
                 ("w_a", C.c_float), ("w_delta", C.c_float), ("w_da", C.c_float),
                 ("w_ddelta", C.c_float), ("w_x", C.c_float), ("w_y", C.c_float),
                 ("w_yaw", C.c_float), ("w_v", C.c_float), ("max_iter", C.c_int),
-                ("du_th", C.c_float), ("max_ls", C.c_int)]
+                ("du_th", C.c_float), ("max_ls", C.c_int), ("j_tol", C.c_float)]
 
 
 # name -> (restype, argtypes); every symbol include/crb.h declares

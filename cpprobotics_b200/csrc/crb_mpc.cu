@@ -33,6 +33,7 @@ struct MpcP {
   int max_iter;
   float du_th;
   int max_ls;
+  float j_tol;
 };
 
 #define REG_EPS 1.0e-3f
@@ -124,7 +125,7 @@ __device__ __forceinline__ void box_qp2(float Q00, float Q01, float Q11, float g
   if (sa1) r.k1 = sa1lo ? lo1 : hi1;
   if (sa0 && sa1) { r.cl0 = true; r.cl1 = true; return; }
   if (sa0) {
-    r.H11 = Q11 > REG_EPS ? Q11 : REG_EPS;
+    r.H11 = fabsf(Q11) > REG_EPS ? fabsf(Q11) : REG_EPS;
     r.ih11 = 1.0f / r.H11;
     float uj = -(fmaf(Q01, r.k0, g1) * r.ih11);
     bool cj = false;
@@ -134,7 +135,7 @@ __device__ __forceinline__ void box_qp2(float Q00, float Q01, float Q11, float g
     return;
   }
   if (sa1) {
-    r.H00 = Q00 > REG_EPS ? Q00 : REG_EPS;
+    r.H00 = fabsf(Q00) > REG_EPS ? fabsf(Q00) : REG_EPS;
     r.ih00 = 1.0f / r.H00;
     float uj = -(fmaf(Q01, r.k1, g0) * r.ih00);
     bool cj = false;
@@ -145,7 +146,7 @@ __device__ __forceinline__ void box_qp2(float Q00, float Q01, float Q11, float g
   }
   const float mh = 0.5f * (Q00 + Q11), dh = 0.5f * (Q00 - Q11);
   const float lam = mh - sqrtf(fmaf(dh, dh, Q01 * Q01));
-  const float shift = lam < REG_EPS ? REG_EPS - lam : 0.0f;
+  const float shift = lam < REG_EPS ? (-lam > REG_EPS ? -lam : REG_EPS) - lam : 0.0f;
   const float H00 = Q00 + shift, H11 = Q11 + shift, H01 = Q01;
   const float det = fmaf(H00, H11, -(H01 * H01));
   const float idet = 1.0f / det, ih00 = 1.0f / H00, ih11 = 1.0f / H11;
@@ -599,7 +600,7 @@ __device__ __forceinline__ float direct_cost(int T, int64_t n, int64_t i, const 
   return J;
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 crb_mpc_solve_kernel(int64_t count, int64_t ld_in, int T, const float* __restrict__ x0,
                      const float* __restrict__ xref, const float* __restrict__ u_init,
                      float* __restrict__ XA, float* __restrict__ XB, float* __restrict__ UA,
@@ -640,19 +641,22 @@ crb_mpc_solve_kernel(int64_t count, int64_t ld_in, int T, const float* __restric
     st = CRB_MPC_NONFINITE;
   } else {
     bool gn = false;  // Newton sweep; Gauss-Newton retry after a failed line search
+    float Jc = J0;    // running cost
     while (it_count < p.max_iter) {
       backward_sweep(T, n, i, X, U, xref, ox, oy, p, gn, G);
       ++it_count;
-      bool accepted = false, small = false;
+      bool accepted = false, tiny = false;
+      int jacc = 0;
       float dJ = 0.0f, du = 0.0f, alpha = 1.0f;
       for (int j = 0; j <= p.max_ls; ++j) {
         forward_sweep(T, n, i, yaw0, v0, X, U, xref, ox, oy, G, alpha, p, Xn, Un, dJ, du);
-        if (dJ < 0.0f) { accepted = true; break; }
-        if (j == 0 && du <= p.du_th) { small = true; break; }  // full step below tolerance
+        if (j == 0) tiny = (du <= p.du_th) || (fabsf(dJ) <= p.j_tol * fabsf(Jc));
+        if (dJ < 0.0f) { accepted = true; jacc = j; break; }
+        if (tiny) break;
         alpha = alpha * 0.5f;
       }
-      if (small) { st = CRB_MPC_CONVERGED; break; }
       if (!accepted) {
+        if (tiny) { st = CRB_MPC_CONVERGED; break; }
         if (!gn) { gn = true; continue; }
         st = CRB_MPC_NO_DESCENT;
         break;
@@ -660,7 +664,8 @@ crb_mpc_solve_kernel(int64_t count, int64_t ld_in, int T, const float* __restric
       gn = false;
       float* tx = X; X = Xn; Xn = tx;
       float* tu = U; U = Un; Un = tu;
-      if (du <= p.du_th) { st = CRB_MPC_CONVERGED; break; }
+      Jc = Jc + dJ;
+      if ((jacc == 0 && tiny) || du <= p.du_th) { st = CRB_MPC_CONVERGED; break; }
     }
   }
   const float J = direct_cost(T, n, i, X, U, xref, ox, oy, p);
@@ -700,6 +705,7 @@ static void mpc_fill(MpcP* p, const crb_mpc_params* prm) {
   p->max_iter = prm->max_iter;
   p->du_th = prm->du_th;
   p->max_ls = prm->max_ls;
+  p->j_tol = prm->j_tol;
 }
 
 static size_t mpc_scratch_floats(int T) { return (size_t)8 * T + (size_t)(4 + NGAIN) * (T - 1); }

@@ -159,6 +159,8 @@ typedef struct crb_mpc_params {
                           reference defines but never uses.) */
   float du_th;         /* stop when sum_t |du_t| <= du_th; default 1e-4 (converged to the NLP optimum) */
   int   max_ls;        /* step halvings per iteration, default 8 (no reference counterpart) */
+  float j_tol;         /* also stop when the full step changes the cost by <= j_tol * cost (default 1e-6,
+                          i.e. ~16 ulp of the binary32 cost: it cannot be resolved any further) */
 } crb_mpc_params;
 void crb_mpc_default_params(crb_mpc_params* p);
 

@@ -27,7 +27,8 @@
  *       as (q'-q)(q'+q) so that it is accurate in binary32)
  *     (if no alpha decreases the cost, the sweep is redone once in Gauss-Newton mode, i.e. without the
  *      second-derivative terms, which always yields a descent direction)
- *   until sum|dU| <= du_th  (or neither mode decreases the cost: stationary to binary32 resolution)
+ *   until sum|dU| <= du_th, or the full step changes the cost by <= j_tol * cost (binary32 cannot
+ *   resolve more), or neither mode decreases the cost
  *
  * ARITHMETIC CONTRACT shared with the CUDA kernel: binary32 throughout; every a*b+c that is meant
  * to be fused is written fmaf(); nothing else may be contracted (gcc -ffp-contract=off, nvcc
@@ -49,6 +50,7 @@
 
 #include <stdio.h>
 int crb_oracle_mpc_trace = 0; /* debugging aid: print one line per outer iteration to stderr */
+int64_t crb_oracle_mpc_nfw_hist[64][16]; /* debugging aid: [outer iteration][forward sweeps used] */
 
 /* ---- sin/cos: Cody-Waite reduction by pi/2 + Cephes-style minimax polynomials ------------------- */
 void crb_oracle_sincosf(float x, float* sn, float* cs) {
@@ -176,7 +178,8 @@ typedef struct {
 /* Projected-Newton step for min 0.5 u'Qu + g'u over the box [lo, hi]^2 (which contains 0); Q may be
  * indefinite.  1. Inputs that sit on a bound with the gradient pushing outward are fixed first
  * (Bertsekas' strongly active set).  2. The Hessian of the remaining inputs is made positive definite
- * (1-D: max(Qjj, eps); 2-D: eigenvalue shift).  3. The convex box QP in those inputs is solved exactly:
+ * using the curvature MAGNITUDE (1-D: max(|Qjj|, eps); 2-D: shift so that the smallest eigenvalue
+ * becomes max(|lam_min|, eps)), so that a noise-level gradient gives a noise-level step.  3. The convex box QP in those inputs is solved exactly:
  * interior point if feasible, else the best of the four clamped edge minimisers (edge order u0 = lo0,
  * hi0, u1 = lo1, hi1; strict '<' keeps the first). */
 static void box_qp2(float Q00, float Q01, float Q11, const float g[2], const float lo[2],
@@ -190,7 +193,7 @@ static void box_qp2(float Q00, float Q01, float Q11, const float g[2], const flo
   if (sa1) r->k[1] = sa1lo ? lo[1] : hi[1];
   if (sa0 && sa1) { r->cl[0] = 1; r->cl[1] = 1; return; }
   if (sa0) { /* u1 free, 1-D */
-    r->H11 = Q11 > REG_EPS ? Q11 : REG_EPS;
+    r->H11 = fabsf(Q11) > REG_EPS ? fabsf(Q11) : REG_EPS; /* curvature magnitude */
     r->ih11 = 1.0f / r->H11;
     float uj = -(fmaf(Q01, r->k[0], g[1]) * r->ih11);
     int cj = 0;
@@ -200,7 +203,7 @@ static void box_qp2(float Q00, float Q01, float Q11, const float g[2], const flo
     return;
   }
   if (sa1) { /* u0 free, 1-D */
-    r->H00 = Q00 > REG_EPS ? Q00 : REG_EPS;
+    r->H00 = fabsf(Q00) > REG_EPS ? fabsf(Q00) : REG_EPS;
     r->ih00 = 1.0f / r->H00;
     float uj = -(fmaf(Q01, r->k[1], g[0]) * r->ih00);
     int cj = 0;
@@ -212,7 +215,8 @@ static void box_qp2(float Q00, float Q01, float Q11, const float g[2], const flo
   /* both free: shift to positive definite, then the convex 2-D box QP */
   const float mh = 0.5f * (Q00 + Q11), dh = 0.5f * (Q00 - Q11);
   const float lam = mh - sqrtf(fmaf(dh, dh, Q01 * Q01));
-  const float shift = lam < REG_EPS ? REG_EPS - lam : 0.0f;
+  /* smallest eigenvalue -> max(|lam|, eps): steps scale with the curvature magnitude */
+  const float shift = lam < REG_EPS ? (-lam > REG_EPS ? -lam : REG_EPS) - lam : 0.0f;
   const float H00 = Q00 + shift, H11 = Q11 + shift, H01 = Q01;
   const float det = fmaf(H00, H11, -(H01 * H01));
   const float idet = 1.0f / det, ih00 = 1.0f / H00, ih11 = 1.0f / H11;
@@ -530,24 +534,33 @@ void crb_oracle_mpc_solve(int T, const float x0_in[4], const float* xref_flat /*
     status = CRB_ORACLE_MPC_NONFINITE;
   } else {
     int gn = 0; /* 0: Newton (exact second derivatives); 1: Gauss-Newton retry after a failed search */
+    float Jc = J0; /* running cost: J0 plus the accepted differences */
     while (iters < p->max_iter) {
       backward_sweep(T, (const float(*)[4])X, (const float(*)[2])U, (const float(*)[4])xref, p, gn,
                      gains);
       ++iters;
-      int accepted = 0, small = 0;
+      int accepted = 0, tiny = 0, jacc = 0;
       float dJ = 0.0f, du = 0.0f, alpha = 1.0f;
       for (int j = 0; j <= p->max_ls; ++j) {
         forward_sweep(T, x0, (const float(*)[4])X, (const float(*)[2])U, (const float(*)[4])xref,
                       gains, alpha, p, Xn, Un, &dJ, &du);
-        if (dJ < 0.0f) { accepted = 1; break; }
-        if (j == 0 && du <= p->du_th) { small = 1; break; } /* full step below tolerance: converged */
+        /* the FULL step moves the inputs by <= du_th, or the cost by less than binary32 can resolve */
+        if (j == 0) tiny = (du <= p->du_th) || (fabsf(dJ) <= p->j_tol * fabsf(Jc));
+        if (dJ < 0.0f) { accepted = 1; jacc = j; break; }
+        if (tiny) break;
         alpha = alpha * 0.5f;
       }
-      if (crb_oracle_mpc_trace)
-        fprintf(stderr, "  it %d gn %d accepted %d alpha %g dJ %.3e du %.3e\n", iters, gn, accepted,
-                (double)alpha, (double)dJ, (double)du);
-      if (small) { status = CRB_ORACLE_MPC_CONVERGED; break; }
+      if (crb_oracle_mpc_trace == 2) {
+        int nf = 0; float a2 = 1.0f; while (a2 > alpha && nf < 14) { a2 *= 0.5f; ++nf; }
+        nf = accepted || tiny ? nf + 1 : nf;
+#pragma omp atomic
+        crb_oracle_mpc_nfw_hist[iters < 64 ? iters - 1 : 63][nf < 16 ? nf : 15]++;
+      }
+      if (crb_oracle_mpc_trace == 1)
+        fprintf(stderr, "  it %d gn %d accepted %d tiny %d alpha %g dJ %.3e du %.3e J %.6f\n", iters, gn,
+                accepted, tiny, (double)alpha, (double)dJ, (double)du, (double)Jc);
       if (!accepted) {
+        if (tiny) { status = CRB_ORACLE_MPC_CONVERGED; break; }
         if (!gn) { gn = 1; continue; }
         status = CRB_ORACLE_MPC_NO_DESCENT;
         break;
@@ -555,7 +568,8 @@ void crb_oracle_mpc_solve(int T, const float x0_in[4], const float* xref_flat /*
       gn = 0;
       float(*tx)[4] = X; X = Xn; Xn = tx;
       float(*tu)[2] = U; U = Un; Un = tu;
-      if (du <= p->du_th) { status = CRB_ORACLE_MPC_CONVERGED; break; }
+      Jc = Jc + dJ;
+      if ((jacc == 0 && tiny) || du <= p->du_th) { status = CRB_ORACLE_MPC_CONVERGED; break; }
     }
   }
   const float J = direct_cost(T, (const float(*)[4])X, (const float(*)[2])U, (const float(*)[4])xref, p);

@@ -20,6 +20,7 @@ typedef struct crb_oracle_mpc_params {
   int max_iter;
   float du_th;
   int max_ls;
+  float j_tol;
 } crb_oracle_mpc_params;
 
 void crb_oracle_sincosf(float x, float* sn, float* cs);

@@ -21,7 +21,7 @@ import numpy as np
 REG_EPS = 1.0e-3
 DEFAULTS = dict(dt=0.2, wb=2.5, max_steer=np.deg2rad(45.0), max_accel=1.0, max_speed=55.0 / 3.6,
                 min_speed=-20.0 / 3.6, w_a=0.01, w_delta=0.01, w_da=0.01, w_ddelta=1.0, w_x=1.0,
-                w_y=1.0, w_yaw=0.5, w_v=0.5, max_iter=50, du_th=1e-4, max_ls=8)
+                w_y=1.0, w_yaw=0.5, w_v=0.5, max_iter=50, du_th=1e-4, max_ls=8, j_tol=1e-6)
 
 
 def f_dyn(x, u, p):
@@ -89,7 +89,7 @@ def box_qp2(H, g, lo, hi):
         return u, np.array([True, True]), Hr
     if sa.any():
         i = int(np.argmax(sa)); j = 1 - i
-        Hr[j, j] = max(H[j, j], REG_EPS)
+        Hr[j, j] = max(abs(H[j, j]), REG_EPS)          # curvature magnitude (saddle-free Newton)
         uj = -(g[j] + H[j, i] * u[i]) / Hr[j, j]
         cj = False
         if uj <= lo[j]:
@@ -100,8 +100,8 @@ def box_qp2(H, g, lo, hi):
         cl = np.array([True, True]); cl[j] = cj
         return u, cl, Hr
     lam = np.linalg.eigvalsh(H)[0]
-    if lam < REG_EPS:
-        Hr = H + (REG_EPS - lam) * np.eye(2)
+    if lam < REG_EPS:                                   # smallest eigenvalue -> max(|lam|, eps)
+        Hr = H + (max(-lam, REG_EPS) - lam) * np.eye(2)
     u = -np.linalg.solve(Hr, g)
     if np.all(u >= lo) and np.all(u <= hi):
         return u, np.array([False, False]), Hr
@@ -229,30 +229,31 @@ def box_ilqr(x0, xref, p=None, U_init=None):
     while iters < p["max_iter"]:
         ks, Ks, dV1, dV2 = backward(X, U, xref, p, gauss_newton=gn)
         iters += 1
-        accepted = False
-        small = False
+        accepted = tiny = False
+        jacc = 0
         for j in range(p["max_ls"] + 1):
             Xn, Un = forward(x0, X, U, ks, Ks, 0.5 ** j, p)
             Jn = nlp_cost(Xn, Un, xref, p)
+            du = np.abs(Un - U).sum()
+            if j == 0:   # full step below the input tolerance, or below the cost resolution
+                tiny = du <= p["du_th"] or abs(Jn - J) <= p["j_tol"] * abs(J)
             if Jn < J:
-                accepted = True
+                accepted, jacc = True, j
                 break
-            if j == 0 and np.abs(Un - U).sum() <= p["du_th"]:
-                small = True      # the full step is already below the tolerance: converged
+            if tiny:
                 break
-        if small:
-            status = 0
-            break
         if not accepted:
+            if tiny:
+                status = 0
+                break
             if not gn:          # Newton step found no descent: retry this iterate with Gauss-Newton
                 gn = True
                 continue
             status = 2
             break
         gn = False
-        du = np.abs(Un - U).sum()
         X, U, J = Xn, Un, Jn
-        if du <= p["du_th"]:
+        if (jacc == 0 and tiny) or du <= p["du_th"]:
             status = 0
             break
     return dict(X=X, U=U, cost=J, status=status, iters=iters)
