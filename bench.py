@@ -150,15 +150,25 @@ def max_over_ranks(ms: float, world: int) -> float:
     return float(t.item())
 
 
+def max_over_ranks_cpu(ms: float, world: int) -> float:
+    """gloo flavour of max_over_ranks for the CPU multi-process tests."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([ms], dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
 def gather_stats(stats, world):
     """The single collective of the data path: all-gather of CRB_STATS_LEN doubles per rank."""
     import torch
     if world == 1:
         return stats.unsqueeze(0)
     import torch.distributed as dist
-    out = torch.empty((world, stats.numel()), dtype=stats.dtype, device=stats.device)
-    dist.all_gather_into_tensor(out, stats)
-    return out
+    out = torch.empty(world * stats.numel(), dtype=stats.dtype, device=stats.device)
+    dist.all_gather_into_tensor(out, stats.contiguous().view(-1))
+    return out.view(world, stats.numel())
 
 
 def pinned(a):

@@ -341,3 +341,15 @@ int64_t crb_oracle_check_ff_product(double pre, uint32_t lo_bits, uint32_t hi_bi
   }
   return bad;
 }
+
+/* raw Philox4x32-10 block (for the known-answer vectors of the Random123 distribution) */
+void crb_oracle_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]};
+  uint32_t k[2] = {key[0], key[1]};
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k);
+    k[0] += 0x9E3779B9u;
+    k[1] += 0xBB67AE85u;
+  }
+  for (int i = 0; i < 4; ++i) out[i] = c[i];
+}
