@@ -55,20 +55,30 @@ crb_stats_partial_kernel(int64_t n, int64_t i0, const float* __restrict__ values
   }
 }
 
-__global__ void crb_stats_combine_kernel(int nblocks, int64_t n, const double* __restrict__ partial,
-                                         double* __restrict__ out) {
-  const int k = threadIdx.x;
-  if (k == 7) {
-    out[7] = (double)n;
-    return;
+// One CTA of ST_BLOCKS threads: thread b takes block b's partial, then a fixed shuffle/shared-memory
+// tree (same shape every run -> bit-reproducible).
+__global__ void __launch_bounds__(ST_BLOCKS)
+crb_stats_combine_kernel(int64_t n, const double* __restrict__ partial, double* __restrict__ out) {
+  __shared__ double sm[7][ST_BLOCKS / 32];
+  const int b = threadIdx.x, lane = b & 31, wid = b >> 5;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    double t = partial[(size_t)b * 8 + k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double other = __shfl_down_sync(0xffffffffu, t, o);
+      t = k == 1 ? fmin(t, other) : (k == 2 ? fmax(t, other) : t + other);
+    }
+    if (lane == 0) sm[k][wid] = t;
   }
-  if (k > 7) return;
-  double t = partial[k];
-  for (int b = 1; b < nblocks; ++b) {
-    const double o = partial[(size_t)b * 8 + k];
-    t = k == 1 ? fmin(t, o) : (k == 2 ? fmax(t, o) : t + o);
+  __syncthreads();
+  if (b < 7) {
+    double t = sm[b][0];
+    for (int w = 1; w < ST_BLOCKS / 32; ++w)
+      t = b == 1 ? fmin(t, sm[b][w]) : (b == 2 ? fmax(t, sm[b][w]) : t + sm[b][w]);
+    out[b] = t;
   }
-  out[k] = t;
+  if (b == 7) out[7] = (double)n;
 }
 
 extern "C" int crb_stats_reduce(crb_ctx* ctx, int64_t n, int64_t i0, const float* values,
@@ -80,7 +90,7 @@ extern "C" int crb_stats_reduce(crb_ctx* ctx, int64_t n, int64_t i0, const float
   double* partial = (double*)ctx->scratch;
   crb_stats_partial_kernel<<<ST_BLOCKS, ST_THREADS, 0, ctx->stream>>>(n, i0, values, status, iters,
                                                                       partial);
-  crb_stats_combine_kernel<<<1, 32, 0, ctx->stream>>>(ST_BLOCKS, n, partial, stats_dev);
+  crb_stats_combine_kernel<<<1, ST_BLOCKS, 0, ctx->stream>>>(n, partial, stats_dev);
   CRB_CUDA(cudaGetLastError());
   ctx->launches += 2;
   return CRB_OK;

@@ -1,0 +1,238 @@
+// reference_api.hpp — host C++ with the reference's own names, argument order and value semantics,
+// on top of the C ABI (crb.h).  A CppRobotics main() re-targets to the B200 engine by including this
+// header instead of <Eigen/Eigen> for the hot functions and linking libcrb.so.
+//
+//   ekf_estimation(xEst, PEst, z, u, Q, R)        src/extended_kalman_filter.cpp:64-78
+//   pf_localization(px, pw, xEst, PEst, z, u, Rsim, Q, gen, gaussian_d)   src/particle_filter.cpp:73-109
+//   mpc_solve(x0, traj_ref)                       src/model_predictive_control.cpp:255-346
+//   update(state, a, delta)                       src/model_predictive_control.cpp:69-81
+//   calc_ref_trajectory(...)                      src/model_predictive_control.cpp:130-170
+//
+// Eigen is not a dependency: crb::Mat<R,C> is a POD with the memory layout of
+// Eigen::Matrix<float,R,C> (column-major, contiguous, no padding), enough of its interface for the
+// call sites above.  Errors: the reference reports none; these shims throw std::runtime_error with
+// crb_last_error_string() (e.g. when no B200 is present: there is no CPU fallback).
+//
+// These are single-agent calls (n = 1, or NP particles) through the *_host entry points: they exist for
+// drop-in compatibility and for tests; throughput comes from calling the batched C ABI directly.
+#ifndef CRB_REFERENCE_API_HPP_
+#define CRB_REFERENCE_API_HPP_
+
+#include <array>
+#include <cmath>
+#include <cstring>
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../crb.h"
+
+namespace crb {
+
+template <int R, int C = 1>
+struct Mat {
+  float d[R * C];
+  float& operator()(int r, int c = 0) { return d[r + R * c]; }
+  const float& operator()(int r, int c = 0) const { return d[r + R * c]; }
+  float* data() { return d; }
+  const float* data() const { return d; }
+  static constexpr int rows() { return R; }
+  static constexpr int cols() { return C; }
+  static Mat Zero() {
+    Mat m;
+    for (int i = 0; i < R * C; ++i) m.d[i] = 0.0f;
+    return m;
+  }
+  static Mat Identity() {
+    Mat m = Zero();
+    for (int i = 0; i < (R < C ? R : C); ++i) m(i, i) = 1.0f;
+    return m;
+  }
+};
+using Vector2f = Mat<2, 1>;
+using Vector4f = Mat<4, 1>;
+using Matrix2f = Mat<2, 2>;
+using Matrix4f = Mat<4, 4>;
+using RowVector3f = Mat<1, 3>;
+template <int T>
+using M_XREF = Mat<4, T>;  // Eigen::Matrix<float, NX, T>, src/model_predictive_control.cpp:52
+
+inline void check(int rc, const char* what) {
+  if (rc != CRB_OK)
+    throw std::runtime_error(std::string(what) + " failed (" + std::to_string(rc) +
+                             "): " + crb_last_error_string());
+}
+
+// One lazily created context per thread (a crb_ctx is not thread-safe).
+class Session {
+ public:
+  static crb_ctx* get() {
+    thread_local Session s;
+    return s.ctx_;
+  }
+  Session(const Session&) = delete;
+
+ private:
+  Session() { check(crb_init(&ctx_, -1), "crb_init"); }
+  ~Session() { crb_destroy(ctx_); }
+  crb_ctx* ctx_ = nullptr;
+};
+
+}  // namespace crb
+
+namespace cpprobotics {
+// include/cpprobotics_types.h:19-21
+using Vec_f = std::vector<float>;
+using Poi_f = std::array<float, 2>;
+using Vec_Poi = std::vector<Poi_f>;
+// include/motion_model.h:31-42 (same members, same constructor, no default constructor)
+struct State {
+  float x;
+  float y;
+  float yaw;
+  float v;
+  State(float x_, float y_, float yaw_, float v_) : x(x_), y(y_), yaw(yaw_), v(v_) {}
+};
+}  // namespace cpprobotics
+
+// ---------------------------------------------------------------------------------------------------
+// Reference-signature functions (global namespace, like the reference's free functions).
+// ---------------------------------------------------------------------------------------------------
+
+// src/extended_kalman_filter.cpp:64-78.  Q and R are passed through (the reference's DT stays 0.1).
+inline void ekf_estimation(crb::Vector4f& xEst, crb::Matrix4f& PEst, crb::Vector2f z,
+                           crb::Vector2f u, crb::Matrix4f Q, crb::Matrix2f R) {
+  crb_ekf_params prm;
+  crb_ekf_default_params(&prm);
+  std::memcpy(prm.Q, Q.data(), sizeof(prm.Q));
+  std::memcpy(prm.R, R.data(), sizeof(prm.R));
+  // n = 1: SoA and AoS coincide, the Eigen column-major buffers are passed as they are
+  crb::check(crb_ekf_step_batched_host(crb::Session::get(), 1, xEst.data(), PEst.data(), z.data(),
+                                       u.data(), &prm, 1),
+             "crb_ekf_step_batched_host");
+}
+
+// src/model_predictive_control.cpp:69-81
+inline void update(cpprobotics::State& state, float a, float delta) {
+  crb_ctx* ctx = crb::Session::get();
+  float st[4] = {state.x, state.y, state.yaw, state.v}, u0[2] = {a, delta};
+  void *dst = nullptr, *du = nullptr;
+  crb::check(crb_device_alloc(ctx, &dst, sizeof(st)), "crb_device_alloc");
+  crb::check(crb_device_alloc(ctx, &du, sizeof(u0)), "crb_device_alloc");
+  crb::check(crb_memcpy_h2d(ctx, dst, st, sizeof(st)), "crb_memcpy_h2d");
+  crb::check(crb_memcpy_h2d(ctx, du, u0, sizeof(u0)), "crb_memcpy_h2d");
+  crb_mpc_params prm;
+  crb_mpc_default_params(&prm);
+  crb::check(crb_mpc_plant_update_batched(ctx, 1, (float*)dst, (const float*)du, &prm),
+             "crb_mpc_plant_update_batched");
+  crb::check(crb_memcpy_d2h(ctx, st, dst, sizeof(st)), "crb_memcpy_d2h");
+  crb_device_free(ctx, dst);
+  crb_device_free(ctx, du);
+  state.x = st[0]; state.y = st[1]; state.yaw = st[2]; state.v = st[3];
+}
+
+// src/model_predictive_control.cpp:255-346.  Returns the reference's vector
+// [x(T) | y(T) | yaw(T) | v(T) | delta(T-1) | a(T-1)] (:54-60, :341-345); the caller reads
+// output[a_start] and output[delta_start] (:376).
+template <int T>
+inline cpprobotics::Vec_f mpc_solve(cpprobotics::State x0, crb::M_XREF<T> traj_ref,
+                                    const crb_mpc_params* params = nullptr,
+                                    int32_t* status_out = nullptr) {
+  static_assert(T >= 2 && T <= CRB_MPC_MAX_T, "horizon out of range");
+  crb_mpc_params prm;
+  if (params) prm = *params; else crb_mpc_default_params(&prm);
+  const float x[4] = {x0.x, x0.y, x0.yaw, x0.v};
+  cpprobotics::Vec_f result(4 * T + 2 * (T - 1));
+  int32_t status = 0;
+  // M_XREF is column-major 4 x T: element (k, t) at k + 4t, which is exactly field 4t + k for n = 1
+  crb::check(crb_mpc_solve_batched_host(crb::Session::get(), 1, T, x, traj_ref.data(), nullptr, &prm,
+                                        result.data(), nullptr, nullptr, &status, nullptr),
+             "crb_mpc_solve_batched_host");
+  if (status_out) *status_out = status;
+  return result;
+}
+
+// src/model_predictive_control.cpp:130-170 (calc_nearest_index :107-127 inside).  ck is accepted and
+// ignored like in the reference.
+template <int T>
+inline void calc_ref_trajectory(cpprobotics::State state, cpprobotics::Vec_f cx,
+                                cpprobotics::Vec_f cy, cpprobotics::Vec_f cyaw,
+                                cpprobotics::Vec_f /*ck*/, cpprobotics::Vec_f sp, float dl,
+                                int& target_ind, crb::M_XREF<T>& xref) {
+  crb_ctx* ctx = crb::Session::get();
+  const size_t nc = cx.size();
+  const float st[4] = {state.x, state.y, state.yaw, state.v};
+  int32_t ti = target_ind;
+  void *dcourse = nullptr, *dst = nullptr, *dti = nullptr, *dxr = nullptr;
+  crb::check(crb_device_alloc(ctx, &dcourse, 4 * nc * sizeof(float)), "crb_device_alloc");
+  crb::check(crb_device_alloc(ctx, &dst, sizeof(st)), "crb_device_alloc");
+  crb::check(crb_device_alloc(ctx, &dti, sizeof(ti)), "crb_device_alloc");
+  crb::check(crb_device_alloc(ctx, &dxr, 4 * T * sizeof(float)), "crb_device_alloc");
+  float* dc = (float*)dcourse;
+  crb::check(crb_memcpy_h2d(ctx, dc, cx.data(), nc * sizeof(float)), "h2d");
+  crb::check(crb_memcpy_h2d(ctx, dc + nc, cy.data(), nc * sizeof(float)), "h2d");
+  crb::check(crb_memcpy_h2d(ctx, dc + 2 * nc, cyaw.data(), nc * sizeof(float)), "h2d");
+  crb::check(crb_memcpy_h2d(ctx, dc + 3 * nc, sp.data(), nc * sizeof(float)), "h2d");
+  crb::check(crb_memcpy_h2d(ctx, dst, st, sizeof(st)), "h2d");
+  crb::check(crb_memcpy_h2d(ctx, dti, &ti, sizeof(ti)), "h2d");
+  crb_mpc_params prm;
+  crb_mpc_default_params(&prm);
+  crb::check(crb_mpc_calc_ref_trajectory_batched(ctx, 1, T, (const float*)dst, dc, dc + nc,
+                                                 dc + 2 * nc, dc + 3 * nc, (int32_t)nc, dl,
+                                                 (int32_t*)dti, (float*)dxr, &prm),
+             "crb_mpc_calc_ref_trajectory_batched");
+  crb::check(crb_memcpy_d2h(ctx, xref.data(), dxr, 4 * T * sizeof(float)), "d2h");
+  crb::check(crb_memcpy_d2h(ctx, &ti, dti, sizeof(ti)), "d2h");
+  crb_device_free(ctx, dcourse); crb_device_free(ctx, dst);
+  crb_device_free(ctx, dti); crb_device_free(ctx, dxr);
+  target_ind = ti;
+}
+
+// src/particle_filter.cpp:73-109.  NP is a template parameter (a macro in the reference, :21).
+// gen and gaussian_d are taken BY VALUE exactly like the reference (:78), so the caller's generator is
+// not advanced; the draws are made here on the host in the reference's order (two per particle,
+// :87-88) and handed to the kernel as its explicit noise input.
+template <int NP>
+inline void pf_localization(crb::Mat<4, NP>& px, crb::Mat<NP, 1>& pw, crb::Vector4f& xEst,
+                            crb::Matrix4f& PEst, std::vector<crb::RowVector3f> z, crb::Vector2f u,
+                            crb::Matrix2f Rsim, float Q, std::mt19937 gen,
+                            std::normal_distribution<> gaussian_d) {
+  crb_ctx* ctx = crb::Session::get();
+  crb_pf_params prm;
+  crb_pf_default_params(&prm);
+  prm.Q = Q;
+  prm.rsim_diag[0] = Rsim(0, 0);
+  prm.rsim_diag[1] = Rsim(1, 1);
+  prm.u[0] = u(0);
+  prm.u[1] = u(1);
+  // Eigen's px is 4 x NP column-major = AoS per particle; the engine wants SoA [4][NP]
+  std::vector<float> sx(4 * NP), noise(2 * NP), lm(3 * z.size());
+  for (int ip = 0; ip < NP; ++ip) {
+    for (int k = 0; k < 4; ++k) sx[k * NP + ip] = px(k, ip);
+    noise[ip] = (float)gaussian_d(gen);
+    noise[NP + ip] = (float)gaussian_d(gen);
+  }
+  for (size_t i = 0; i < z.size(); ++i)
+    for (int k = 0; k < 3; ++k) lm[3 * i + k] = z[i](0, k);
+  void *dpx = nullptr, *dpw = nullptr, *dn = nullptr;
+  crb::check(crb_device_alloc(ctx, &dpx, sx.size() * sizeof(float)), "crb_device_alloc");
+  crb::check(crb_device_alloc(ctx, &dpw, NP * sizeof(float)), "crb_device_alloc");
+  crb::check(crb_device_alloc(ctx, &dn, noise.size() * sizeof(float)), "crb_device_alloc");
+  crb::check(crb_memcpy_h2d(ctx, dpx, sx.data(), sx.size() * sizeof(float)), "h2d");
+  crb::check(crb_memcpy_h2d(ctx, dpw, pw.data(), NP * sizeof(float)), "h2d");
+  crb::check(crb_memcpy_h2d(ctx, dn, noise.data(), noise.size() * sizeof(float)), "h2d");
+  crb::check(crb_pf_predict_weight_batched(ctx, NP, (float*)dpx, (float*)dpw, (const float*)dn, 0,
+                                           lm.data(), (int)z.size(), &prm),
+             "crb_pf_predict_weight_batched");                          // :81-102
+  crb::check(crb_pf_estimate(ctx, NP, (const float*)dpx, (float*)dpw, xEst.data(), PEst.data(),
+                             nullptr),
+             "crb_pf_estimate");                                        // :104-107
+  crb::check(crb_memcpy_d2h(ctx, sx.data(), dpx, sx.size() * sizeof(float)), "d2h");
+  crb::check(crb_memcpy_d2h(ctx, pw.data(), dpw, NP * sizeof(float)), "d2h");
+  for (int ip = 0; ip < NP; ++ip)
+    for (int k = 0; k < 4; ++k) px(k, ip) = sx[k * NP + ip];
+  crb_device_free(ctx, dpx); crb_device_free(ctx, dpw); crb_device_free(ctx, dn);
+}
+
+#endif  // CRB_REFERENCE_API_HPP_

@@ -1,0 +1,90 @@
+"""The C++ host layer with the reference's own signatures (include/crb/reference_api.hpp).
+CPU: it compiles as C++11 against the C ABI, links libcrb.so, and fails loudly without a GPU.
+GPU: a reference-style main() (tests/cpp/ref_api_demo.cpp) reproduces the oracle."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from cpprobotics_b200 import _lib, synth
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "cpp", "ref_api_demo.cpp")
+K, T, NP = 40, 6, 100
+
+
+def build(tmp_path):
+    exe = str(tmp_path / "ref_api_demo")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call(["g++", "-std=c++11", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), SRC,
+                           "-L", libdir, "-lcrb", f"-Wl,-rpath,{libdir}", "-o", exe])
+    return exe
+
+
+def make_inputs():
+    x, P, z, u = synth.ekf_inputs(1, seed=77, n_steps=K)
+    zu = np.stack([z[0::2, 0], z[1::2, 0], u[0::2, 0], u[1::2, 0]], axis=1).astype(np.float32)  # per step
+    course = synth.mpc_course(length=120.0)
+    st = np.array([10.2, 20 * np.sin(10.2 / 20) + 0.4, 0.6, 2.5], np.float32)
+    px, pw, _ = synth.pf_inputs(NP, seed=77)
+    lm = synth.pf_landmarks(4, seed=77)
+    buf = [np.float32([K]), zu.reshape(-1), np.float32([len(course[0])]), *course, st, np.float32([5]),
+           px.T.reshape(-1), pw, np.float32([len(lm)]), lm.reshape(-1), np.float32([1234])]
+    return np.concatenate([np.asarray(b, np.float32).reshape(-1) for b in buf]), zu, course, st, px, pw, lm
+
+
+def test_compiles_links_and_fails_loudly_without_gpu(tmp_path):
+    import torch
+    exe = build(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the failure path is covered on the CPU box")
+    blob = make_inputs()[0]
+    blob.tofile(tmp_path / "in.bin")
+    r = subprocess.run([exe, str(tmp_path / "in.bin"), str(tmp_path / "out.bin")], capture_output=True, text=True)
+    assert r.returncode == 3 and "no CPU fallback" in r.stderr
+    assert not os.path.exists(tmp_path / "out.bin")
+
+
+@pytest.mark.gpu
+def test_reference_style_main_matches_oracle(tmp_path):
+    exe = build(tmp_path)
+    blob, zu, course, st, px, pw, lm = make_inputs()
+    blob.tofile(tmp_path / "in.bin")
+    subprocess.check_call([exe, str(tmp_path / "in.bin"), str(tmp_path / "out.bin")])
+    out = np.fromfile(tmp_path / "out.bin", np.float32)
+    p = 0
+
+    def take(n):
+        nonlocal p
+        v = out[p:p + n]; p += n
+        return v
+    # EKF: config 1 plumbing (one agent, K steps through ekf_estimation)
+    xg, Pg = take(4), take(16)
+    xo, Po = np.zeros(4, np.float32), np.eye(4, dtype=np.float32).reshape(-1)
+    for k in range(K):
+        xo, Po = O.ekf_estimation(xo, Po, zu[k, :2], zu[k, 2:])
+    assert np.abs(xg - xo).max() <= 1e-5 * np.abs(xo).max() and np.abs(Pg - Po).max() <= 1e-5 * np.abs(Po).max()
+    # calc_ref_trajectory: integer index work bit-exact
+    xr, ti = take(4 * T), int(take(1)[0])
+    xro, tio = O.calc_ref_trajectory(st, *course, 1.0, T, 5)
+    assert ti == tio and np.array_equal(xr, xro.reshape(-1))       # col-major 4xT == [T][4]
+    # mpc_solve: bit-exact vs the oracle (reference return layout), status word
+    sol, status = take(4 * T + 2 * (T - 1)), int(take(1)[0])
+    ro = O.mpc_solve_batched(st.reshape(4, 1), xro.reshape(-1, 1), T)
+    assert np.array_equal(sol, ro["sol"][:, 0]) and status == ro["status"][0]
+    # update(): plant step on the first control
+    sg = take(4)
+    so = O.plant_update(st, ro["u0"][0, 0], ro["u0"][1, 0])
+    assert np.abs(sg - so).max() <= 1e-5 * np.abs(so).max()
+    # pf_localization with the reference's by-value generator
+    pxg, pwg, xeg, Peg, noise = take(4 * NP).reshape(NP, 4).T, take(NP), take(4), take(16), take(2 * NP)
+    nz = np.stack([noise[0::2], noise[1::2]])
+    pxo, pwo = O.pf_predict_weight_batched(px, pw, nz, lm)
+    assert np.abs(pxg - pxo).max() <= 1e-5 * max(1.0, np.abs(pxo).max())
+    pwn, xeo, Peo, _ = O.pf_estimate(pxo, pwo)
+    assert np.abs(pwg - pwn).max() <= 2e-3 * np.abs(pwn).max()       # weight conditioning, see DESIGN.md 3.2
+    assert np.abs(xeg - xeo).max() <= 1e-3 and np.abs(Peg - Peo.T.reshape(-1)).max() <= 1e-3
+    assert p == out.size
