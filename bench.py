@@ -41,7 +41,7 @@ PF_N = 1 << 20
 PF_LM = 8
 MPC_N = 1 << 16
 MPC_T = 20
-MPC_ITER, MPC_DUTH, MPC_LS = 50, 1e-4, 8   # IPOPT's max_iter (:326); tight du so the NLP converges
+MPC_ITER, MPC_DUTH, MPC_LS = 50, 1e-4, 4   # IPOPT's max_iter (:326); tight du so the NLP converges
 EKF_BYTES = 176       # read x4 P16 z2 u2, write x4 P16 (f32)            SURVEY §8 d-3
 PF_BYTES = 48         # read px4 w1 noise2, write px4 w1                  SURVEY §8 d-4
 MPC_BYTES = 344 + 472 # read x0 4 + xref 80, write sol 118 + u0 2 (+cost,status,iters 3) f32 ~ 828
@@ -123,6 +123,8 @@ def dist_setup(n_gpus: int):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"     # keep stdout to the one JSON line
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     else:

@@ -180,7 +180,7 @@ void crb_mpc_default_params(crb_mpc_params* p) {
   p->w_v = 0.5f;
   p->max_iter = 50;   // IPOPT's max_iter option (:326); MAX_ITER 3 / DU_TH 0.1 (:30-31) are unused macros
   p->du_th = 1.0e-4f;
-  p->max_ls = 8;
+  p->max_ls = 4;
   p->j_tol = 1.0e-6f;
 }
 

@@ -158,7 +158,8 @@ typedef struct crb_mpc_params {
                           reference gives IPOPT (:326).  (MAX_ITER 3 :30 and DU_TH 0.1 :31 are macros the
                           reference defines but never uses.) */
   float du_th;         /* stop when sum_t |du_t| <= du_th; default 1e-4 (converged to the NLP optimum) */
-  int   max_ls;        /* step halvings per iteration, default 8 (no reference counterpart) */
+  int   max_ls;        /* step halvings per iteration, default 4: alpha = 1 .. 1/16, then the Gauss-Newton retry
+                          (no reference counterpart) */
   float j_tol;         /* also stop when the full step changes the cost by <= j_tol * cost (default 1e-6,
                           i.e. ~16 ulp of the binary32 cost: it cannot be resolved any further) */
 } crb_mpc_params;

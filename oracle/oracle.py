@@ -167,7 +167,7 @@ def mpc_params(**over) -> MpcParams:
     d = dict(dt=0.2, wb=2.5, max_steer=np.float32(45.0 / 180 * np.pi), max_accel=1.0,
              max_speed=np.float32(55.0 / 3.6), min_speed=np.float32(-20.0 / 3.6), w_a=0.01,
              w_delta=0.01, w_da=0.01, w_ddelta=1.0, w_x=1.0, w_y=1.0, w_yaw=0.5, w_v=0.5,
-             max_iter=50, du_th=1e-4, max_ls=8, j_tol=1e-6)
+             max_iter=50, du_th=1e-4, max_ls=4, j_tol=1e-6)
     d.update(over)
     p = MpcParams()
     for k, v in d.items():

@@ -53,7 +53,8 @@ int main(int argc, char** argv) {
     for (auto& v : cy) v = rd();
     for (auto& v : cyaw) v = rd();
     for (auto& v : sp) v = rd();
-    State state(rd(), rd(), rd(), rd());
+    const float sx = rd(), sy = rd(), syaw = rd(), sv = rd();  // (argument evaluation order is unspecified)
+    State state(sx, sy, syaw, sv);
     int target_ind = (int)rd();
     crb::M_XREF<T> xref;
     calc_ref_trajectory<T>(state, cx, cy, cyaw, ck, sp, 1.0f, target_ind, xref);

@@ -21,7 +21,7 @@ import numpy as np
 REG_EPS = 1.0e-3
 DEFAULTS = dict(dt=0.2, wb=2.5, max_steer=np.deg2rad(45.0), max_accel=1.0, max_speed=55.0 / 3.6,
                 min_speed=-20.0 / 3.6, w_a=0.01, w_delta=0.01, w_da=0.01, w_ddelta=1.0, w_x=1.0,
-                w_y=1.0, w_yaw=0.5, w_v=0.5, max_iter=50, du_th=1e-4, max_ls=8, j_tol=1e-6)
+                w_y=1.0, w_yaw=0.5, w_v=0.5, max_iter=50, du_th=1e-4, max_ls=4, j_tol=1e-6)
 
 
 def f_dyn(x, u, p):

@@ -1,5 +1,7 @@
 """GPU parity tests proper: the CUDA path, called through the C ABI (libcrb.so), against the CPU
 oracle on the same seeded inputs.  Run with `-m gpu` on a B200."""
+import os
+
 import numpy as np
 import pytest
 
@@ -319,3 +321,28 @@ def test_stats_reduce(engine):
     assert out[4] == (status == 0).sum() and out[5] == iters.sum() and out[7] == n
     chk = (v[ok].astype(np.float64) * (((1000 + np.arange(n))[ok] % 251) + 1)).sum()
     assert abs(out[6] - chk) < 1e-7 * n
+
+
+def test_ekf_tma_staged_variant_is_bitwise_the_direct_kernel(engine, tmp_path):
+    """CRB_EKF_VARIANT=4 selects the cp.async.bulk + mbarrier pipelined kernel (same ekf_step code): the
+    results must be bit-identical to the default kernel.  The variant is latched per process, so the
+    staged kernel runs in a child process."""
+    import subprocess
+    import sys
+    import torch
+    n = 300_004          # many tiles per CTA, ragged last tile (multiple of 4)
+    x, P, z, u = synth.ekf_inputs(n)
+    xd, Pd, zd, ud = _dev(x, P, z, u)
+    engine.ekf_estimation(xd, Pd, zd, ud)
+    torch.cuda.synchronize()
+    code = ("import sys, numpy as np, torch; sys.path.insert(0, %r)\n"
+            "from cpprobotics_b200 import Engine, synth\n"
+            "x, P, z, u = synth.ekf_inputs(%d)\n"
+            "e = Engine(0); t = [torch.from_numpy(a).cuda() for a in (x, P, z, u)]\n"
+            "e.ekf_estimation(*t); torch.cuda.synchronize()\n"
+            "np.savez(%r, x=t[0].cpu().numpy(), P=t[1].cpu().numpy())\n") % (
+                os.path.dirname(os.path.dirname(os.path.abspath(__file__))), n, str(tmp_path / "o.npz"))
+    env = dict(os.environ, CRB_EKF_VARIANT="4")
+    subprocess.check_call([sys.executable, "-c", code], env=env)
+    o = np.load(tmp_path / "o.npz")
+    assert np.array_equal(o["x"], xd.cpu().numpy()) and np.array_equal(o["P"], Pd.cpu().numpy())
