@@ -74,6 +74,8 @@ PROTOTYPES = {
                                                      C.POINTER(PfParams)]),
     "crb_pf_estimate": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p]),
+    "crb_pf_resample": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_uint64, C.c_float, C.c_void_p, C.c_void_p]),
     "crb_mpc_default_params": (None, [C.POINTER(MpcParams)]),
     "crb_mpc_solve_batched": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.POINTER(MpcParams), C.c_void_p, C.c_void_p,

@@ -171,6 +171,21 @@ class Engine:
               "crb_pf_estimate")
         return xe, pe.reshape(4, 4).T.copy(), sw.value
 
+    def pf_resample(self, px, pw, uniforms=None, seed: int = 0, nth: Optional[float] = None, px_tmp=None):
+        """resampling() :120-148.  In place on px [4,n], pw [n]; returns (did_resample, Neff)."""
+        n = int(px.shape[-1])
+        _shape(px, 4, n, "px"); _shape(pw, 1, n, "pw")
+        if px_tmp is None:
+            px_tmp = torch.empty_like(px)
+        did = C.c_int(0)
+        neff = C.c_double(0.0)
+        check(self.lib.crb_pf_resample(
+            self.ctx, n, _ptr(px, np.float32, device=True, name="px"), _ptr(pw, np.float32, device=True, name="pw"),
+            _ptr(px_tmp, np.float32, device=True, name="px_tmp"),
+            _ptr(uniforms, np.float32, device=True, name="uniforms"), C.c_uint64(int(seed)),
+            C.c_float(n / 2 if nth is None else nth), C.addressof(did), C.addressof(neff)), "crb_pf_resample")
+        return bool(did.value), neff.value
+
     # ---- MPC --------------------------------------------------------------------------------------
     def _mpc(self, fn, dev, x0, xref, T, params, u_init, sol, u0, cost, status, iters):
         n = int(x0.shape[-1])

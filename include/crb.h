@@ -11,6 +11,7 @@
  *                                         (motion_model :26-40, gauss_likelihood :53-57)
  *   crb_pf_estimate                     <- pf_localization() tail            src/particle_filter.cpp:104-107
  *                                         (calc_covariance :59-71)
+ *   crb_pf_resample                     <- resampling() + cumsum()           src/particle_filter.cpp:111-148
  *   crb_mpc_solve_batched[_host]        <- mpc_solve() + FG_EVAL            src/model_predictive_control.cpp:188-346
  *   crb_mpc_plant_update_batched        <- update()                          src/model_predictive_control.cpp:69-81
  *   crb_mpc_calc_ref_trajectory_batched <- calc_ref_trajectory() :130-170 + calc_nearest_index() :107-127
@@ -139,6 +140,19 @@ int crb_pf_predict_weight_batched_host(crb_ctx* ctx, int64_t n, float* px, float
  * independent of the launch geometry.  sum_w_out (optional) receives the pre-normalisation sum. */
 int crb_pf_estimate(crb_ctx* ctx, int64_t n, const float* px, float* pw, float* xEst_host,
                     float* PEst_host, double* sum_w_out_host);
+
+/* Low-variance resampling when the effective particle count drops (device pointers).
+ *   Neff = 1 / sum(pw^2); if Neff < nth (the reference's NTh = NP/2, :22): cumulative weights, one
+ *   uniform draw per particle in [1,2) (the reference's uni_d, :242 - the offset by 1/NP is its quirk),
+ *   resampleid_j = j/NP + U_j/NP (:133), for each j the first index whose cumulative weight reaches it,
+ *   capped at NP-1 (:136-143), gather, and pw = 1/NP (:147).  px is updated in place (px_tmp [4][n] is
+ *   workspace).  uniforms [n] are explicit inputs in [1,2), or NULL to draw them from Philox4x32-10(seed,
+ *   particle index).  The cumulative sum is accumulated in double (the reference sums 100 floats in
+ *   float).  *did_resample_host (optional) receives 0/1, *neff_host (optional) Neff.
+ * Replaces: resampling() + cumsum(), src/particle_filter.cpp:111-148. */
+int crb_pf_resample(crb_ctx* ctx, int64_t n, float* px, float* pw, float* px_tmp,
+                    const float* uniforms, uint64_t seed, float nth, int* did_resample_host,
+                    double* neff_host);
 
 /* ---- MPC -------------------------------------------------------------------------------------- */
 /* Problem constants: src/model_predictive_control.cpp:23-48 (macros), cost weights :202-210 and

@@ -353,3 +353,69 @@ void crb_oracle_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_
   }
   for (int i = 0; i < 4; ++i) out[i] = c[i];
 }
+
+/* ---- resampling() + cumsum(): src/particle_filter.cpp:111-148 ----------------------------------------
+ * px [4][n] SoA, pw [n], uniforms [n]: the uni_d(gen) draws in [1,2) (:242), in particle order.
+ * reference_mode = 1 reproduces the reference's float arithmetic exactly (float dot product for Neff,
+ * float sequential cumsum of pw and of Ones*1.0/NP for `base`); reference_mode = 0 is the batched engine's
+ * statement (sum of squares and cumulative sum accumulated in double, base(j) = j/n), which is what makes
+ * sense for 10^6 particles.  Returns 1 when resampling happened (Neff < nth). */
+int crb_oracle_pf_resample(int64_t n, float* px, float* pw, const double* uniforms, float nth,
+                           int reference_mode, float* neff_out) {
+  float neff;
+  if (reference_mode) {
+    float dot = pw[0] * pw[0];
+    for (int64_t i = 1; i < n; ++i) dot = dot + pw[i] * pw[i];
+    neff = (float)(1.0 / (double)dot);                                   /* :126 */
+  } else {
+    double dot = 0.0;
+    for (int64_t i = 0; i < n; ++i) dot += (double)pw[i] * (double)pw[i];
+    neff = (float)(1.0 / (double)(float)dot);
+  }
+  if (neff_out) *neff_out = neff;
+  if (!(neff < nth)) return 0;                                           /* :127 */
+  float* wcum = (float*)malloc((size_t)n * sizeof(float));
+  float* base = (float*)malloc((size_t)n * sizeof(float));
+  float* out = (float*)malloc((size_t)4 * n * sizeof(float));
+  if (reference_mode) {
+    const float inc = (float)1.0 / (float)n;                             /* Ones()*1.0/NP element */
+    wcum[0] = pw[0];
+    float c = pw[0] * 0.0f + inc;                                        /* pw*0.0 + Ones*1.0/NP (:130) */
+    base[0] = c - inc;
+    for (int64_t i = 1; i < n; ++i) {
+      wcum[i] = wcum[i - 1] + pw[i];                                     /* cumsum :111-118 */
+      c = c + (pw[i] * 0.0f + inc);
+      base[i] = c - inc;
+    }
+  } else {
+    double run = 0.0;
+    for (int64_t i = 0; i < n; ++i) {
+      run += (double)pw[i];
+      wcum[i] = (float)run;
+      base[i] = (float)((double)i / (double)n);
+    }
+  }
+  int64_t ind = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const float rid = (float)((double)base[i] + uniforms[i] / (double)n); /* :133 */
+    while (rid > wcum[ind] && ind < n - 1) ind += 1;                     /* :136-138 */
+    for (int f = 0; f < 4; ++f) out[f * n + i] = px[f * n + ind];        /* :139 */
+  }
+  memcpy(px, out, (size_t)4 * n * sizeof(float));                        /* :145 */
+  const float wn = reference_mode ? (float)1.0 / (float)n : (float)(1.0 / (double)n);
+  for (int64_t i = 0; i < n; ++i) pw[i] = wn;                            /* :146 */
+  free(wcum); free(base); free(out);
+  return 1;
+}
+
+/* the uniform the CUDA kernel draws when uniforms == NULL: Philox4x32-10(seed, j), counter word 2 tagged */
+double crb_oracle_philox_uniform12(uint64_t seed, uint64_t index) {
+  uint32_t c[4] = {(uint32_t)index, (uint32_t)(index >> 32), 0x5EED5EEDu, 0u};
+  uint32_t k[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k);
+    k[0] += 0x9E3779B9u;
+    k[1] += 0xBB67AE85u;
+  }
+  return (double)(1.0f + (float)(c[0] >> 9) * 1.1920928955078125e-07f);
+}

@@ -57,6 +57,10 @@ void crb_oracle_pf_predict_weight_batched(int64_t n, float* px, float* pw, const
 void crb_oracle_pf_estimate(int64_t n, const float* px, float* pw, float xEst[4], float PEst[16],
                             double* sum_w);
 
+/* resampling() + cumsum() :111-148 (see crb_oracle.c) */
+int crb_oracle_pf_resample(int64_t n, float* px, float* pw, const double* uniforms, float nth,
+                           int reference_mode, float* neff_out);
+double crb_oracle_philox_uniform12(uint64_t seed, uint64_t index);
 void crb_oracle_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 int crb_oracle_num_threads(void);
 /* verification aids for arithmetic shortcuts of the CUDA PF kernel (see crb_oracle.c) */

@@ -141,6 +141,27 @@ def pf_predict_weight_batched(px, pw, noise, landmarks, seed=0, consts=None, nth
     return px, pw
 
 
+def pf_resample(px, pw, uniforms, nth=None, reference_mode=False):
+    """resampling() :120-148.  uniforms [n] in [1,2).  Returns (px, pw, did_resample, neff)."""
+    L = lib()
+    L.crb_oracle_pf_resample.restype = C.c_int
+    L.crb_oracle_pf_resample.argtypes = [C.c_int64, f32p, f32p, f64p, C.c_float, C.c_int, C.POINTER(C.c_float)]
+    px = np.ascontiguousarray(px, np.float32).copy()
+    pw = np.ascontiguousarray(pw, np.float32).copy()
+    n = px.shape[1]
+    neff = C.c_float(0.0)
+    did = L.crb_oracle_pf_resample(n, px, pw, np.ascontiguousarray(uniforms, np.float64),
+                                   float(n // 2 if nth is None else nth), int(reference_mode), C.byref(neff))
+    return px, pw, bool(did), neff.value
+
+
+def philox_uniform12(seed, index):
+    L = lib()
+    L.crb_oracle_philox_uniform12.restype = C.c_double
+    L.crb_oracle_philox_uniform12.argtypes = [C.c_uint64, C.c_uint64]
+    return L.crb_oracle_philox_uniform12(int(seed), int(index))
+
+
 def pf_estimate(px, pw):
     px = np.ascontiguousarray(px, np.float32)
     pw = np.ascontiguousarray(pw, np.float32).copy()

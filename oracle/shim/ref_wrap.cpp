@@ -58,6 +58,26 @@ void ref_pf_localization(float* px, float* pw, float* xEst, float* PEst, const f
   for (int i = 0; i < 4; ++i) xEst[i] = xe(i);
   for (int i = 0; i < 16; ++i) PEst[i] = Pe.d[i];
 }
+// resampling() :120-148 with a seeded generator passed BY VALUE like main() does (:271); draws[NP] returns the
+// uniforms it consumed (only meaningful when it resampled).  Returns 1 if the weights were reset to 1/NP.
+int ref_resampling(float* px, float* pw, unsigned seed, double* draws) {
+  Eigen::Matrix<float, 4, NP> pxm; Eigen::Matrix<float, NP, 1> pwm;
+  for (int i = 0; i < 4 * NP; ++i) pxm.d[i] = px[i];
+  for (int i = 0; i < NP; ++i) pwm.d[i] = pw[i];
+  std::mt19937 gen2{seed};
+  std::uniform_real_distribution<> uni_d{1.0, 2.0};
+  float before = pwm(0);
+  resampling(pxm, pwm, gen2, uni_d);
+  std::mt19937 g3{seed};
+  std::uniform_real_distribution<> u3{1.0, 2.0};
+  for (int i = 0; i < NP; ++i) draws[i] = u3(g3);
+  int did = 0;
+  for (int i = 0; i < NP; ++i) if (pwm(i) != pw[i]) did = 1;
+  (void)before;
+  for (int i = 0; i < 4 * NP; ++i) px[i] = pxm.d[i];
+  for (int i = 0; i < NP; ++i) pw[i] = pwm.d[i];
+  return did;
+}
 #elif WHICH == 3
 int ref_mpc_T(void) { return T; }
 void ref_update(float* st, float a, float delta) {

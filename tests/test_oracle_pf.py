@@ -121,3 +121,25 @@ def test_golden_vectors():
     assert np.abs(pxo - g["px_out"]).max() <= 1e-6
     ok = g["pw_out"] > 1e-30
     assert (np.abs(pwo[ok] - g["pw_out"][ok]) / g["pw_out"][ok]).max() <= 1e-3   # libm-dependent, see above
+
+
+def test_resample_batched_mode_properties():
+    """The batched statement (double cumulative sum, base = j/n): survivors are existing particles, heavy
+    particles are duplicated about n*w times, weights reset to 1/n, nothing happens when Neff >= nth."""
+    n = 20000
+    px, pw, noise = synth.pf_inputs(n)
+    lm = synth.pf_landmarks(8)
+    pxo, pwo = O.pf_predict_weight_batched(px, pw, noise, lm)
+    pwn = O.pf_estimate(pxo, pwo)[0]
+    u = np.array([O.philox_uniform12(5, j) for j in range(n)])
+    assert u.min() >= 1.0 and u.max() < 2.0
+    px2, pw2, did, neff = O.pf_resample(pxo, pwn, u)
+    assert did and abs(neff - 1.0 / np.sum(pwn.astype(np.float64) ** 2)) < 1e-3 * neff
+    assert np.all(pw2 == np.float32(1.0 / n))
+    keys = {tuple(c) for c in pxo.T}
+    assert all(tuple(c) in keys for c in px2.T[::97])
+    top = int(np.argmax(pwn))
+    copies = int((px2.T == pxo[:, top]).all(axis=1).sum())
+    assert abs(copies - n * pwn[top]) <= 2
+    px3, pw3, did3, _ = O.pf_resample(px, np.full(n, 1.0 / n, np.float32), u)
+    assert not did3 and np.array_equal(px3, px)

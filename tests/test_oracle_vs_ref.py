@@ -147,3 +147,23 @@ def test_nlp_statement_equals_fg_eval_and_solution_satisfies_it():
         g = fg[1:].reshape(4, T)                        # rows x, y, yaw, v; column 0 = initial state
         assert np.array_equal(g[:, 0].astype(np.float32), st[:, i])
         assert np.abs(g[:, 1:]).max() < 5e-5            # dynamics residuals :242-245 (float32 roll-out)
+
+
+def test_resampling_restatement_is_bitwise_the_reference_text():
+    """resampling() + cumsum() (:111-148) of the reference's own source against oracle.pf_resample in
+    reference_mode, on peaked weights (Neff < NP/2 -> resample) and on flat ones (no resample)."""
+    L = _load("libref_pf.so")
+    L.ref_resampling.restype = C.c_int
+    L.ref_resampling.argtypes = [f32p, f32p, C.c_uint, f64p]
+    NP = 100
+    for seed, sharp in ((1, True), (2, True), (3, False)):
+        px, pw, noise = synth.pf_inputs(NP, seed=seed)
+        lm = synth.pf_landmarks(4, seed=seed)
+        if sharp:
+            px, pw = O.pf_predict_weight_batched(px, pw, noise, lm)
+            pw = (pw / np.float32(pw.sum())).astype(np.float32)
+        pxr, pwr, draws = np.ascontiguousarray(px.T.reshape(-1)).copy(), pw.copy(), np.zeros(NP)
+        did_r = L.ref_resampling(pxr, pwr, 99 + seed, draws)
+        pxo, pwo, did_o, neff = O.pf_resample(px, pw, draws, reference_mode=True)
+        assert bool(did_r) == did_o == sharp
+        assert np.array_equal(pxr.reshape(NP, 4).T, pxo) and np.array_equal(pwr, pwo)
