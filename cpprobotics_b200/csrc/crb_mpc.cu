@@ -16,7 +16,7 @@
 // oracle/crb_oracle_mpc.c; this kernel reproduces it BIT FOR BIT (explicit fmaf, -fmad=false,
 // polynomial sin/cos, IEEE divide/sqrt), so status words and iteration counts match exactly.
 //
-// Mapping: ONE THREAD PER PROBLEM.  The matrices are 4x4 / 2x4 / 2x2 with five non-trivial entries
+// Mapping: ONE THREAD PER PROBLEM (workspace CTA-interleaved, see MPC_BLOCK below).  The matrices are 4x4 / 2x4 / 2x2 with five non-trivial entries
 // in A and two in B: a warp per problem would idle >80 % of its lanes and pay shuffles for every
 // product, whereas a thread per problem keeps the whole stage in registers, runs pure FFMA with
 // ample ILP, and makes every global access a coalesced 128-byte line because all per-problem data
@@ -38,6 +38,13 @@ struct MpcP {
 
 #define REG_EPS 1.0e-3f
 #define NGAIN 14  // k[2], Kx[2][4], Kw[2][2]
+// Solver workspace layout: CTA-interleaved.  A CTA of MPC_BLOCK threads owns a contiguous slab
+// [item][MPC_BLOCK]; thread t of the CTA reads item k at slab[k*MPC_BLOCK + t].  Accesses stay coalesced
+// (MPC_BLOCK consecutive floats per item) and every per-thread offset is a COMPILE-TIME constant times the
+// item index, so loads/stores use immediate offsets instead of two 64-bit adds each (address arithmetic
+// was the largest instruction class of the first version of this kernel).
+#define MPC_BLOCK 128
+#define LS MPC_BLOCK
 
 // sin/cos: Cody-Waite reduction by pi/2 + minimax polynomials (same operations as the oracle's
 // crb_oracle_sincosf; libm / CUDA sinf are NOT used so that CPU and GPU agree to the bit).
@@ -192,12 +199,12 @@ __device__ __forceinline__ void box_qp2(float Q00, float Q01, float Q11, float g
 // ---- backward sweep -------------------------------------------------------------------------------
 // X [4T][n], U [2(T-1)][n] (field 2t+c, c = 0 delta, 1 a), xref [4T][n] (course frame; ox, oy are
 // subtracted on the fly), gains out G [14(T-1)][n].
-__device__ __forceinline__ void backward_sweep(int T, int64_t n, int64_t i,
-                                               const float* __restrict__ X,
+// X [4T], U [2(T-1)] (item 2t+c, c = 0 delta, 1 a), XR [4T] (reference, already translated by
+// (ox, oy)), gains out G [14(T-1)]: thread pointers into the CTA-interleaved workspace, item stride LS.
+__device__ __forceinline__ void backward_sweep(int T, const float* __restrict__ X,
                                                const float* __restrict__ U,
-                                               const float* __restrict__ xref, float ox,
-                                               float oy, const MpcP& p, bool gn,
-                                               float* __restrict__ G) {
+                                               const float* __restrict__ XR, const MpcP& p,
+                                               bool gn, float* __restrict__ G) {
   const int N = T - 1;
   const float R2[2] = {2.0f * p.w_delta, 2.0f * p.w_a};
   const float Rd2[2] = {2.0f * p.w_ddelta, 2.0f * p.w_da};
@@ -212,31 +219,25 @@ __device__ __forceinline__ void backward_sweep(int T, int64_t n, int64_t i,
   }
   Pww[0][0] = Pww[0][1] = Pww[1][0] = Pww[1][1] = 0.0f;
   pw[0] = pw[1] = 0.0f;
-  {
-    const float off[4] = {ox, oy, 0.0f, 0.0f};
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float xr = k < 2 ? xref[((int64_t)N * 4 + k) * n + i] - off[k]
-                             : xref[((int64_t)N * 4 + k) * n + i];
-      px[k] = Q2[k] * (X[((int64_t)N * 4 + k) * n + i] - xr);
-    }
-  }
+  for (int k = 0; k < 4; ++k) px[k] = Q2[k] * (X[(N * 4 + k) * LS] - XR[(N * 4 + k) * LS]);
   // Software pipeline: the operands of stage t-1 are requested at the top of stage t so that their
   // L2/HBM latency hides under stage t's arithmetic (the sweep is a 19-long dependent chain).
   float ut[2];                   // U[t]
   float xt[4], xr[4], um[2];     // X[t], xref[t] (translated), U[t-1]
-  ut[0] = U[((int64_t)(N - 1) * 2 + 0) * n + i];
-  ut[1] = U[((int64_t)(N - 1) * 2 + 1) * n + i];
+  ut[0] = U[((N - 1) * 2 + 0) * LS];
+  ut[1] = U[((N - 1) * 2 + 1) * LS];
   auto load_stage = [&](int t, float (&x_)[4], float (&r_)[4], float (&m_)[2]) {
+    const float* xs = X + t * 4 * LS;
+    const float* rs = XR + t * 4 * LS;
+    const float* us = U + (t - 1) * 2 * LS;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) x_[k] = X[((int64_t)t * 4 + k) * n + i];
+    for (int k = 0; k < 4; ++k) x_[k] = xs[k * LS];
     if (t >= 1) {
-      r_[0] = xref[((int64_t)t * 4 + 0) * n + i] - ox;
-      r_[1] = xref[((int64_t)t * 4 + 1) * n + i] - oy;
-      r_[2] = xref[((int64_t)t * 4 + 2) * n + i];
-      r_[3] = xref[((int64_t)t * 4 + 3) * n + i];
-      m_[0] = U[((int64_t)(t - 1) * 2 + 0) * n + i];
-      m_[1] = U[((int64_t)(t - 1) * 2 + 1) * n + i];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) r_[k] = rs[k * LS];
+      m_[0] = us[0];
+      m_[1] = us[LS];
     } else {
       r_[0] = r_[1] = r_[2] = r_[3] = 0.0f;
       m_[0] = m_[1] = 0.0f;
@@ -384,11 +385,11 @@ __device__ __forceinline__ void backward_sweep(int T, int64_t n, int64_t i,
     }
     // store gains for the forward sweeps
     {
-      float* g = G + ((int64_t)t * NGAIN) * n + i;
-      g[0 * n] = k0; g[1 * n] = k1;
+      float* g = G + t * NGAIN * LS;
+      g[0 * LS] = k0; g[1 * LS] = k1;
 #pragma unroll
-      for (int b = 0; b < 4; ++b) { g[(2 + b) * n] = Kx[0][b]; g[(6 + b) * n] = Kx[1][b]; }
-      g[10 * n] = Kw[0][0]; g[11 * n] = Kw[0][1]; g[12 * n] = Kw[1][0]; g[13 * n] = Kw[1][1];
+      for (int b = 0; b < 4; ++b) { g[(2 + b) * LS] = Kx[0][b]; g[(6 + b) * LS] = Kx[1][b]; }
+      g[10 * LS] = Kw[0][0]; g[11 * LS] = Kw[0][1]; g[12 * LS] = Kw[1][0]; g[13 * LS] = Kw[1][1];
     }
     // value-function update for du = k + Kx dx + Kw dw with the TRUE Quu
     const float m0 = fmaf(Q01, k1, fmaf(Q00, k0, qu[0]));
@@ -476,10 +477,10 @@ __device__ __forceinline__ void backward_sweep(int T, int64_t n, int64_t i,
 }
 
 // ---- forward sweep: clamped roll-out under the affine policy; returns dJ and sum|du| ----------------
-__device__ __forceinline__ void forward_sweep(int T, int64_t n, int64_t i, float yaw0, float v0,
+__device__ __forceinline__ void forward_sweep(int T, float yaw0, float v0,
                                               const float* __restrict__ X,
                                               const float* __restrict__ U,
-                                              const float* __restrict__ xref, float ox, float oy,
+                                              const float* __restrict__ XR,
                                               const float* __restrict__ G, float alpha,
                                               const MpcP& p, float* __restrict__ Xn,
                                               float* __restrict__ Un, float& dJ_out,
@@ -489,23 +490,22 @@ __device__ __forceinline__ void forward_sweep(int T, int64_t n, int64_t i, float
   float xo[4] = {0.0f, 0.0f, yaw0, v0};   // X[t]  (both roll-outs start at x0)
   float unm[2] = {0.0f, 0.0f}, uom[2] = {0.0f, 0.0f};  // Un[t-1], U[t-1]
 #pragma unroll
-  for (int k = 0; k < 4; ++k) Xn[(int64_t)k * n + i] = xn[k];
+  for (int k = 0; k < 4; ++k) Xn[k * LS] = xn[k];
   const float wu[2] = {p.w_delta, p.w_a};
   const float wd[2] = {p.w_ddelta, p.w_da};
   float uo[2], gk[NGAIN], xo1[4], xr1[4];
   auto load_stage = [&](int t, float (&uo_)[2], float (&gk_)[NGAIN], float (&xo1_)[4],
                         float (&xr1_)[4]) {
-    const float* g = G + ((int64_t)t * NGAIN) * n + i;
-    uo_[0] = U[((int64_t)t * 2 + 0) * n + i];
-    uo_[1] = U[((int64_t)t * 2 + 1) * n + i];
+    const float* g = G + t * NGAIN * LS;
+    const float* us = U + t * 2 * LS;
+    const float* xs = X + (t + 1) * 4 * LS;
+    const float* rs = XR + (t + 1) * 4 * LS;
+    uo_[0] = us[0];
+    uo_[1] = us[LS];
 #pragma unroll
-    for (int j = 0; j < NGAIN; ++j) gk_[j] = g[(int64_t)j * n];
+    for (int j = 0; j < NGAIN; ++j) gk_[j] = g[j * LS];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) xo1_[k] = X[((int64_t)(t + 1) * 4 + k) * n + i];
-    xr1_[0] = xref[((int64_t)(t + 1) * 4 + 0) * n + i] - ox;
-    xr1_[1] = xref[((int64_t)(t + 1) * 4 + 1) * n + i] - oy;
-    xr1_[2] = xref[((int64_t)(t + 1) * 4 + 2) * n + i];
-    xr1_[3] = xref[((int64_t)(t + 1) * 4 + 3) * n + i];
+    for (int k = 0; k < 4; ++k) { xo1_[k] = xs[k * LS]; xr1_[k] = rs[k * LS]; }
   };
   load_stage(0, uo, gk, xo1, xr1);
   for (int t = 0; t < T - 1; ++t) {
@@ -534,12 +534,12 @@ __device__ __forceinline__ void forward_sweep(int T, int64_t n, int64_t i, float
     bool s0, s1;
     a_bounds(xn[3], p, alo, ahi, s0, s1);
     u[1] = clampf(u[1], alo, ahi);
-    Un[((int64_t)t * 2 + 0) * n + i] = u[0];
-    Un[((int64_t)t * 2 + 1) * n + i] = u[1];
+    Un[(t * 2 + 0) * LS] = u[0];
+    Un[(t * 2 + 1) * LS] = u[1];
     float xn1[4];
     dyn_step(xn, u[0], u[1], p, xn1);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) Xn[((int64_t)(t + 1) * 4 + k) * n + i] = xn1[k];
+    for (int k = 0; k < 4; ++k) Xn[((t + 1) * 4 + k) * LS] = xn1[k];
     // cost difference, term by term: w (q' - q)(q' + q)
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
@@ -573,13 +573,13 @@ __device__ __forceinline__ void forward_sweep(int T, int64_t n, int64_t i, float
 }
 
 // fg[0] (:199-250) on a stored roll-out, same term order as direct_cost() in the oracle
-__device__ __forceinline__ float direct_cost(int T, int64_t n, int64_t i, const float* X,
-                                             const float* U, const float* xref, float ox, float oy,
-                                             const MpcP& p) {
+__device__ __forceinline__ float direct_cost(int T, const float* __restrict__ X,
+                                             const float* __restrict__ U,
+                                             const float* __restrict__ XR, const MpcP& p) {
   float J = 0.0f;
   float um[2] = {0.0f, 0.0f};
   for (int t = 0; t < T - 1; ++t) {
-    const float d = U[((int64_t)t * 2 + 0) * n + i], a = U[((int64_t)t * 2 + 1) * n + i];
+    const float d = U[(t * 2 + 0) * LS], a = U[(t * 2 + 1) * LS];
     J = fmaf(p.w_delta * d, d, J);
     J = fmaf(p.w_a * a, a, J);
     if (t >= 1) {
@@ -589,10 +589,7 @@ __device__ __forceinline__ float direct_cost(int T, int64_t n, int64_t i, const 
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      float xr = xref[((int64_t)(t + 1) * 4 + k) * n + i];
-      if (k == 0) xr = xr - ox;
-      if (k == 1) xr = xr - oy;
-      const float e = X[((int64_t)(t + 1) * 4 + k) * n + i] - xr;
+      const float e = X[((t + 1) * 4 + k) * LS] - XR[((t + 1) * 4 + k) * LS];
       J = fmaf(p.wq[k] * e, e, J);
     }
     um[0] = d; um[1] = a;
@@ -600,25 +597,41 @@ __device__ __forceinline__ float direct_cost(int T, int64_t n, int64_t i, const 
   return J;
 }
 
-__global__ void __launch_bounds__(128, 4)
+// Workspace items per problem: XA [4T] XB [4T] UA [2N] UB [2N] G [14N] XR [4T]
+__host__ __device__ inline int mpc_ws_items(int T) { return 12 * T + (4 + NGAIN) * (T - 1); }
+
+__global__ void __launch_bounds__(MPC_BLOCK, 4)
 crb_mpc_solve_kernel(int64_t count, int64_t ld_in, int T, const float* __restrict__ x0,
                      const float* __restrict__ xref, const float* __restrict__ u_init,
-                     float* __restrict__ XA, float* __restrict__ XB, float* __restrict__ UA,
-                     float* __restrict__ UB, float* __restrict__ G, int64_t ld_out,
-                     float* __restrict__ sol, float* __restrict__ u0, float* __restrict__ cost,
-                     int32_t* __restrict__ status, int32_t* __restrict__ iters, const MpcP p) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+                     float* __restrict__ ws, int64_t ld_out, float* __restrict__ sol,
+                     float* __restrict__ u0, float* __restrict__ cost, int32_t* __restrict__ status,
+                     int32_t* __restrict__ iters, const MpcP p) {
+  const int64_t i = (int64_t)blockIdx.x * MPC_BLOCK + threadIdx.x;
   if (i >= count) return;
-  const int64_t n = ld_in;  // scratch and inputs share the leading dimension
+  const int64_t n = ld_in;
   const int N = T - 1;
+  // this thread's column of the CTA's workspace slab
+  float* S = ws + (size_t)blockIdx.x * mpc_ws_items(T) * MPC_BLOCK + threadIdx.x;
+  float* X = S;
+  float* Xn = X + 4 * T * LS;
+  float* U = Xn + 4 * T * LS;
+  float* Un = U + 2 * N * LS;
+  float* G = Un + 2 * N * LS;
+  float* XR = G + NGAIN * N * LS;
   const float ox = x0[0 * n + i], oy = x0[1 * n + i];
   const float yaw0 = x0[2 * n + i], v0 = x0[3 * n + i];
-  float* X = XA; float* Xn = XB; float* U = UA; float* Un = UB;
-  // initial clamped roll-out (cold start: zeros, :266-269) in the frame translated to (ox, oy)
+  // reference trajectory into the workspace, translated to the frame of the initial position
+  for (int t = 0; t < T; ++t) {
+    XR[(t * 4 + 0) * LS] = xref[((int64_t)t * 4 + 0) * n + i] - ox;
+    XR[(t * 4 + 1) * LS] = xref[((int64_t)t * 4 + 1) * n + i] - oy;
+    XR[(t * 4 + 2) * LS] = xref[((int64_t)t * 4 + 2) * n + i];
+    XR[(t * 4 + 3) * LS] = xref[((int64_t)t * 4 + 3) * n + i];
+  }
+  // initial clamped roll-out (cold start: zeros, :266-269)
   {
     float x[4] = {0.0f, 0.0f, yaw0, v0};
 #pragma unroll
-    for (int k = 0; k < 4; ++k) X[(int64_t)k * n + i] = x[k];
+    for (int k = 0; k < 4; ++k) X[k * LS] = x[k];
     for (int t = 0; t < N; ++t) {
       float d = u_init ? u_init[(int64_t)t * n + i] : 0.0f;
       float a = u_init ? u_init[(int64_t)(N + t) * n + i] : 0.0f;
@@ -627,29 +640,29 @@ crb_mpc_solve_kernel(int64_t count, int64_t ld_in, int T, const float* __restric
       bool s0, s1;
       a_bounds(x[3], p, alo, ahi, s0, s1);
       a = clampf(a, alo, ahi);
-      U[((int64_t)t * 2 + 0) * n + i] = d;
-      U[((int64_t)t * 2 + 1) * n + i] = a;
+      U[(t * 2 + 0) * LS] = d;
+      U[(t * 2 + 1) * LS] = a;
       float x1[4];
       dyn_step(x, d, a, p, x1);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { x[k] = x1[k]; X[((int64_t)(t + 1) * 4 + k) * n + i] = x1[k]; }
+      for (int k = 0; k < 4; ++k) { x[k] = x1[k]; X[((t + 1) * 4 + k) * LS] = x1[k]; }
     }
   }
   int st = CRB_MPC_MAX_ITER, it_count = 0;
-  const float J0 = direct_cost(T, n, i, X, U, xref, ox, oy, p);
+  const float J0 = direct_cost(T, X, U, XR, p);
   if (!(fabsf(J0) <= 3.0e38f)) {
     st = CRB_MPC_NONFINITE;
   } else {
     bool gn = false;  // Newton sweep; Gauss-Newton retry after a failed line search
     float Jc = J0;    // running cost
     while (it_count < p.max_iter) {
-      backward_sweep(T, n, i, X, U, xref, ox, oy, p, gn, G);
+      backward_sweep(T, X, U, XR, p, gn, G);
       ++it_count;
       bool accepted = false, tiny = false;
       int jacc = 0;
       float dJ = 0.0f, du = 0.0f, alpha = 1.0f;
       for (int j = 0; j <= p.max_ls; ++j) {
-        forward_sweep(T, n, i, yaw0, v0, X, U, xref, ox, oy, G, alpha, p, Xn, Un, dJ, du);
+        forward_sweep(T, yaw0, v0, X, U, XR, G, alpha, p, Xn, Un, dJ, du);
         if (j == 0) tiny = (du <= p.du_th) || (fabsf(dJ) <= p.j_tol * fabsf(Jc));
         if (dJ < 0.0f) { accepted = true; jacc = j; break; }
         if (tiny) break;
@@ -668,24 +681,24 @@ crb_mpc_solve_kernel(int64_t count, int64_t ld_in, int T, const float* __restric
       if ((jacc == 0 && tiny) || du <= p.du_th) { st = CRB_MPC_CONVERGED; break; }
     }
   }
-  const float J = direct_cost(T, n, i, X, U, xref, ox, oy, p);
+  const float J = direct_cost(T, X, U, XR, p);
   if (!(fabsf(J) <= 3.0e38f)) st = CRB_MPC_NONFINITE;
   const int64_t m = ld_out;
   if (sol) {  // the reference's return layout, :54-60
     for (int t = 0; t < T; ++t) {
-      sol[((int64_t)0 * T + t) * m + i] = X[((int64_t)t * 4 + 0) * n + i] + ox;
-      sol[((int64_t)1 * T + t) * m + i] = X[((int64_t)t * 4 + 1) * n + i] + oy;
-      sol[((int64_t)2 * T + t) * m + i] = X[((int64_t)t * 4 + 2) * n + i];
-      sol[((int64_t)3 * T + t) * m + i] = X[((int64_t)t * 4 + 3) * n + i];
+      sol[((int64_t)0 * T + t) * m + i] = X[(t * 4 + 0) * LS] + ox;
+      sol[((int64_t)1 * T + t) * m + i] = X[(t * 4 + 1) * LS] + oy;
+      sol[((int64_t)2 * T + t) * m + i] = X[(t * 4 + 2) * LS];
+      sol[((int64_t)3 * T + t) * m + i] = X[(t * 4 + 3) * LS];
     }
     for (int t = 0; t < N; ++t) {
-      sol[((int64_t)4 * T + t) * m + i] = U[((int64_t)t * 2 + 0) * n + i];
-      sol[((int64_t)4 * T + N + t) * m + i] = U[((int64_t)t * 2 + 1) * n + i];
+      sol[((int64_t)4 * T + t) * m + i] = U[(t * 2 + 0) * LS];
+      sol[((int64_t)4 * T + N + t) * m + i] = U[(t * 2 + 1) * LS];
     }
   }
   if (u0) {  // (a_0, delta_0): what the caller feeds update(), :376
-    u0[0 * m + i] = U[(int64_t)1 * n + i];
-    u0[1 * m + i] = U[(int64_t)0 * n + i];
+    u0[0 * m + i] = U[1 * LS];
+    u0[1 * m + i] = U[0 * LS];
   }
   if (cost) cost[i] = J;
   if (status) status[i] = st;
@@ -708,23 +721,21 @@ static void mpc_fill(MpcP* p, const crb_mpc_params* prm) {
   p->j_tol = prm->j_tol;
 }
 
-static size_t mpc_scratch_floats(int T) { return (size_t)8 * T + (size_t)(4 + NGAIN) * (T - 1); }
+// workspace floats for `count` problems (whole CTAs)
+static size_t mpc_scratch_floats(int T, int64_t count) {
+  const size_t ctas = (size_t)((count + MPC_BLOCK - 1) / MPC_BLOCK);
+  return ctas * (size_t)mpc_ws_items(T) * MPC_BLOCK;
+}
 
-// inputs x0/xref/u_init and the scratch arrays all have leading dimension ld (>= count)
+// inputs x0/xref/u_init have leading dimension ld (>= count); outputs ld_out
 static int mpc_launch(crb_ctx* ctx, cudaStream_t st, int64_t count, int64_t ld, int T,
                       const float* x0, const float* xref, const float* u_init, float* scratch,
                       int64_t ld_out, float* sol, float* u0, float* cost, int32_t* status,
                       int32_t* iters, const crb_mpc_params* prm) {
   MpcP p;
   mpc_fill(&p, prm);
-  float* XA = scratch;
-  float* XB = XA + (size_t)4 * T * ld;
-  float* UA = XB + (size_t)4 * T * ld;
-  float* UB = UA + (size_t)2 * (T - 1) * ld;
-  float* G = UB + (size_t)2 * (T - 1) * ld;
-  const int block = 128;
-  crb_mpc_solve_kernel<<<crb_grid_for(count, block), block, 0, st>>>(
-      count, ld, T, x0, xref, u_init, XA, XB, UA, UB, G, ld_out, sol, u0, cost, status, iters, p);
+  crb_mpc_solve_kernel<<<crb_grid_for(count, MPC_BLOCK), MPC_BLOCK, 0, st>>>(
+      count, ld, T, x0, xref, u_init, scratch, ld_out, sol, u0, cost, status, iters, p);
   CRB_CUDA(cudaGetLastError());
   ctx->launches++;
   return CRB_OK;
@@ -749,7 +760,7 @@ extern "C" int crb_mpc_solve_batched(crb_ctx* ctx, int64_t n, int T, const float
   int rc = mpc_check(ctx, n, T, x0, xref, prm);
   if (rc) return rc;
   if (n == 0) return CRB_OK;
-  rc = crb_ctx_mpc_ws_reserve(ctx, mpc_scratch_floats(T) * (size_t)n * sizeof(float));
+  rc = crb_ctx_mpc_ws_reserve(ctx, mpc_scratch_floats(T, n) * sizeof(float));
   if (rc) return rc;
   return mpc_launch(ctx, ctx->stream, n, n, T, x0, xref, u_init, (float*)ctx->mpc_ws, n, sol,
                     u0, cost, status, iters, prm);
@@ -766,11 +777,11 @@ extern "C" int crb_mpc_solve_batched_host(crb_ctx* ctx, int64_t n, int T, const 
   const int N = T - 1;
   const int64_t chunk_cap = n < (int64_t)32768 ? n : (int64_t)32768;
   const size_t nsol = (size_t)4 * T + 2 * N;
-  // per slot: inputs (4 + 4T + 2N), outputs (nsol + 2 + 1 + 1 + 1), scratch
-  const size_t nf = (size_t)4 + 4 * T + 2 * N + nsol + 5 + mpc_scratch_floats(T);
+  // per slot: inputs (4 + 4T + 2N), outputs (nsol + 2 + 1 + 1 + 1), then the solver workspace
+  const size_t nf = (size_t)4 + 4 * T + 2 * N + nsol + 5;
   const size_t pitch = (size_t)chunk_cap * sizeof(float);
   for (int s = 0; s < CRB_N_PIPE; ++s) {
-    rc = crb_ctx_pipe_reserve(ctx, s, nf * pitch);
+    rc = crb_ctx_pipe_reserve(ctx, s, nf * pitch + mpc_scratch_floats(T, chunk_cap) * sizeof(float));
     if (rc) return rc;
   }
   const size_t hp = (size_t)n * sizeof(float);
