@@ -23,6 +23,7 @@
 // (trajectories, gains) live in SoA scratch arrays indexed [item][problem].  At the BASELINE size
 // (65 536 agents, 128 threads per CTA, <= 128 registers) the whole batch is resident in one wave.
 #include <math.h>
+#include <stdlib.h>
 
 #include "crb_common.cuh"
 
@@ -734,8 +735,48 @@ static int mpc_launch(crb_ctx* ctx, cudaStream_t st, int64_t count, int64_t ld, 
                       int32_t* iters, const crb_mpc_params* prm) {
   MpcP p;
   mpc_fill(&p, prm);
-  crb_mpc_solve_kernel<<<crb_grid_for(count, MPC_BLOCK), MPC_BLOCK, 0, st>>>(
-      count, ld, T, x0, xref, u_init, scratch, ld_out, sol, u0, cost, status, iters, p);
+  // Experiment kept for A/B (CRB_MPC_L2=1): an L2 persisting access-policy window over the solver
+  // workspace.  Measured on B200: 36.1 M solves/s with it vs 60.0 M without (the set-aside shrinks the
+  // normal L2 and the 152 MB workspace thrashes it), so it is OFF by default.
+  static int l2_mode = -1;
+  static size_t l2_max_window = 0, l2_persist = 0;
+  if (l2_mode < 0) {
+    const char* e = getenv("CRB_MPC_L2");
+    l2_mode = e ? atoi(e) : 0;
+    if (l2_mode) {
+      cudaDeviceProp prop;
+      if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+        l2_persist = (size_t)prop.persistingL2CacheMaxSize;
+        l2_max_window = (size_t)prop.accessPolicyMaxWindowSize;
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, l2_persist) != cudaSuccess) l2_mode = 0;
+      } else {
+        l2_mode = 0;
+      }
+      cudaGetLastError();
+    }
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)crb_grid_for(count, MPC_BLOCK));
+  cfg.blockDim = dim3(MPC_BLOCK);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  int nattr = 0;
+  if (l2_mode) {
+    size_t bytes = mpc_scratch_floats(T, count) * sizeof(float);
+    if (bytes > l2_max_window) bytes = l2_max_window;
+    attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[0].val.accessPolicyWindow.base_ptr = scratch;
+    attr[0].val.accessPolicyWindow.num_bytes = bytes;
+    double ratio = bytes ? (double)l2_persist / (double)bytes : 0.0;
+    attr[0].val.accessPolicyWindow.hitRatio = (float)(ratio > 1.0 ? 1.0 : ratio);
+    attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    nattr = 1;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = nattr;
+  CRB_CUDA(cudaLaunchKernelEx(&cfg, crb_mpc_solve_kernel, count, ld, T, x0, xref, u_init, scratch,
+                              ld_out, sol, u0, cost, status, iters, p));
   CRB_CUDA(cudaGetLastError());
   ctx->launches++;
   return CRB_OK;
