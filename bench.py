@@ -478,6 +478,40 @@ def cpu_mpc(st=None, xref=None, sample=8192):
                        "50 ms per solve, model_predictive_control.cpp:328)")
 
 
+def bench_lqr(eng, rank, world, steps, warmup, with_cpu):
+    """Row f-4: 2^20 agents, dlqr of lqr_steer_control.cpp (nx=4, nu=1, <=150 DARE iterations each)."""
+    import torch
+    from cpprobotics_b200 import synth
+    n, nx, nu = 1 << 20, 4, 1
+    dev = torch.device("cuda", torch.cuda.current_device())
+    A, B, Q, R = synth.lqr_inputs(n, nx, i0=rank * n)
+    Ad, Bd, Qd, Rd = (torch.from_numpy(a).to(dev) for a in (A, B, Q, R))
+    K = torch.empty((nu * nx, n), dtype=torch.float32, device=dev)
+    it = torch.empty(n, dtype=torch.int32, device=dev)
+    ms, _ = time_device_steps(lambda k: eng.dlqr(Ad, Bd, Qd, Rd, nx, nu, K=K, iters=it), steps, warmup, world,
+                              eng=eng)
+    mean_it = float(it.float().mean().item())
+    flops = mean_it * 2.0 * (5 * 64 + 2 * 16 + 4 + 16) * n * steps    # 5 4x4x4 + 2 4x4x1 + outer + misc per iter
+    sm_max = float(peaks()[2].get("sm_max_mhz", 1965.0))
+    fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+    out = dict(metric="DARE/LQR gains per second (lqr_steer_control solve_DARE+dlqr, nx=4)",
+               value=world * n * steps / (ms * 1e-3), unit="solves/s", ms_per_step=ms / steps,
+               config=dict(workload="lqr_dlqr_2^20_agents_per_gpu", mean_dare_iters=mean_it),
+               roofline=dict(bound="fp32", achieved=flops / (ms * 1e-3) / 1e12, peak=fp32_peak, unit="TFLOP/s",
+                             frac=flops / (ms * 1e-3) / 1e12 / fp32_peak, traffic=None,
+                             note="no FMA contraction by design (bit-exact with the reference arithmetic): "
+                                  "FMUL+FADD pairs, so 0.5 is the ceiling of this fraction",
+                             kernel="crb_lqr_dlqr_kernel<4,1>"))
+    if with_cpu and rank == 0:
+        from oracle import oracle as O
+        thr = O.num_threads()
+        m = 1 << 16
+        v, calls, el = cpu_time(lambda: O.dlqr_batched(A[:, :m], B[:, :m], Q, R, nx, nu, nthreads=thr), m, budget_s=3.0)
+        out["cpu_baseline"] = dict(value=v, unit="solves/s", cores=thr, kind="port",
+                                   sample=f"{calls} x {m} agents, oracle/crb_oracle.c, OpenMP {thr} threads, {el:.1f} s")
+    return out
+
+
 def traffic_for(name):
     """DRAM bytes per launch from the committed ncu --set full capture (profiles/traffic.json)."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
@@ -500,6 +534,8 @@ def run_ours(args):
         head = bench_ekf(eng, rank, world, args.steps, args.warmup, with_cpu=not args.no_cpu)
         if args.workload in ("all", "pf"):
             res["pf"] = bench_pf(eng, rank, world, args.steps, args.warmup, with_cpu=not args.no_cpu)
+        if args.workload in ("all", "lqr"):
+            res["lqr"] = bench_lqr(eng, rank, world, max(3, args.steps // 5), 3, with_cpu=not args.no_cpu)
         if args.workload in ("all", "mpc"):
             res["mpc"] = bench_mpc(eng, rank, world, max(3, args.steps // 5), max(1, args.warmup // 3),
                                    with_cpu=not args.no_cpu)
@@ -571,7 +607,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="all", choices=["all", "ekf", "pf", "mpc"])
+    ap.add_argument("--workload", default="all", choices=["all", "ekf", "pf", "mpc", "lqr"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -89,6 +89,9 @@ PROTOTYPES = {
                                                       C.c_void_p, C.c_void_p, C.c_void_p,
                                                       C.c_void_p, C.c_int32, C.c_float, C.c_void_p,
                                                       C.c_void_p, C.POINTER(MpcParams)]),
+    "crb_lqr_dlqr_batched": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]),
     "crb_stats_reduce": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p]),
 }

@@ -759,6 +759,17 @@ static int mpc_launch(crb_ctx* ctx, cudaStream_t st, int64_t count, int64_t ld, 
   cfg.gridDim = dim3((unsigned)crb_grid_for(count, MPC_BLOCK));
   cfg.blockDim = dim3(MPC_BLOCK);
   cfg.stream = st;
+  // A/B knob: CRB_MPC_CTAS_PER_SM=k (1..3) caps residency with dummy dynamic shared memory so that the
+  // in-flight working set (k * 128 problems * 2.3 KB per SM) fits in L2.
+  static int smem_cap = -1;
+  if (smem_cap < 0) {
+    const char* e = getenv("CRB_MPC_CTAS_PER_SM");
+    const int k = e ? atoi(e) : 0;
+    smem_cap = (k >= 1 && k <= 3) ? (int)((227 * 1024) / k - 2048) : 0;
+    if (smem_cap > 0)
+      cudaFuncSetAttribute(crb_mpc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap);
+  }
+  cfg.dynamicSmemBytes = (size_t)smem_cap;
   cudaLaunchAttribute attr[1];
   int nattr = 0;
   if (l2_mode) {

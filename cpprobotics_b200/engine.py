@@ -243,6 +243,23 @@ class Engine:
             _ptr(xref, np.float32, device=True, name="xref"), C.byref(prm)),
             "crb_mpc_calc_ref_trajectory_batched")
 
+    # ---- LQR --------------------------------------------------------------------------------------
+    def dlqr(self, A, B, Q, R, nx: int, nu: int, maxiter: int = 150, eps: float = 0.01, K=None, X=None,
+             iters=None):
+        """solve_DARE + dlqr (lqr_steer_control.cpp:75-96 / lqr_speed_steer_control.cpp:85-106).
+        A [nx*nx,n], B [nx*nu,n] per agent, Q [nx*nx], R [nu*nu] shared: CUDA tensors.  Returns K [nu*nx,n]."""
+        n = int(A.shape[-1])
+        _shape(A, nx * nx, n, "A"); _shape(B, nx * nu, n, "B")
+        if K is None:
+            K = torch.empty((nu * nx, n), dtype=torch.float32, device=A.device)
+        check(self.lib.crb_lqr_dlqr_batched(
+            self.ctx, n, int(nx), int(nu), _ptr(A, np.float32, device=True, name="A"),
+            _ptr(B, np.float32, device=True, name="B"), _ptr(Q, np.float32, device=True, name="Q"),
+            _ptr(R, np.float32, device=True, name="R"), int(maxiter), C.c_float(eps),
+            _ptr(K, np.float32, device=True, name="K"), _ptr(X, np.float32, device=True, name="X"),
+            _ptr(iters, np.int32, device=True, name="iters")), "crb_lqr_dlqr_batched")
+        return K
+
     # ---- stats ------------------------------------------------------------------------------------
     def stats_reduce(self, values, status=None, iters=None, i0: int = 0, out=None):
         """Per-GPU summary of a per-agent f32 array -> float64 CUDA tensor of CRB_STATS_LEN."""

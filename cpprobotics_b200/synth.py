@@ -163,3 +163,26 @@ def mpc_xref_numpy(state, pind, T: int, course=None, dl: float = 1.0, dt: float 
         xref[4 * i + 2] = cyaw[j]
         xref[4 * i + 3] = sp[j]
     return np.ascontiguousarray(xref), ind.astype(np.int32)
+
+
+# ---- row f-4: batched LQR (lqr_steer_control.cpp / lqr_speed_steer_control.cpp) ----------------------------
+def lqr_inputs(n: int, nx: int, i0: int = 0, seed: int = 0xC0FFEE, dt: float = 0.1, wheel_base: float = 0.5):
+    """Per-agent (A, B) exactly as lqr_steering_control builds them from the vehicle speed
+    (src/lqr_steer_control.cpp:104-112, src/lqr_speed_steer_control.cpp:116-126), v ~ U(0.3, 4) m/s, plus the
+    reference's Q = I, R = I.  Column-major, float32: A [nx*nx, n], B [nx*nu, n], Q [nx*nx], R [nu*nu]."""
+    assert nx in (4, 5)
+    nu = 1 if nx == 4 else 2
+    idx = np.arange(i0, i0 + n, dtype=np.uint64)
+    v = uniform(seed, 95, idx, 0.3, 4.0).astype(np.float32)
+    A = np.zeros((nx * nx, n), np.float32)
+    B = np.zeros((nx * nu, n), np.float32)
+    A[0 + nx * 0] = 1.0
+    A[0 + nx * 1] = np.float32(dt)
+    A[1 + nx * 2] = v
+    A[2 + nx * 2] = 1.0
+    A[2 + nx * 3] = np.float32(dt)
+    B[3 + nx * 0] = v / np.float32(wheel_base)
+    if nx == 5:
+        A[4 + nx * 4] = 1.0
+        B[4 + nx * 1] = np.float32(dt)
+    return A, B, np.eye(nx, dtype=np.float32).reshape(-1), np.eye(nu, dtype=np.float32).reshape(-1)

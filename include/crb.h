@@ -15,6 +15,8 @@
  *   crb_mpc_solve_batched[_host]        <- mpc_solve() + FG_EVAL            src/model_predictive_control.cpp:188-346
  *   crb_mpc_plant_update_batched        <- update()                          src/model_predictive_control.cpp:69-81
  *   crb_mpc_calc_ref_trajectory_batched <- calc_ref_trajectory() :130-170 + calc_nearest_index() :107-127
+ *   crb_lqr_dlqr_batched                <- solve_DARE() + dlqr()  src/lqr_steer_control.cpp:75-96,
+ *                                          src/lqr_speed_steer_control.cpp:85-106
  *   crb_stats_*                         <- (no reference counterpart) per-GPU summary statistics, the
  *                                          only thing that ever crosses NVLink (one all-gather).
  *
@@ -218,6 +220,17 @@ int crb_mpc_calc_ref_trajectory_batched(crb_ctx* ctx, int64_t n, int T, const fl
                                         const float* sp, int32_t ncourse, float dl,
                                         int32_t* target_ind, float* xref,
                                         const crb_mpc_params* prm);
+
+/* ---- LQR ------------------------------------------------------------------- */
+/* Discrete LQR gain by the reference's fixed-point DARE iteration, one problem per agent.
+ *   (nx, nu) = (4, 1): solve_DARE + dlqr of src/lqr_steer_control.cpp:75-96        (scalar R)
+ *   (nx, nu) = (5, 2): solve_DARE + dlqr of src/lqr_speed_steer_control.cpp:85-106 (2x2 R)
+ *   A [nx*nx][n], B [nx*nu][n]: per-agent, column-major (DEVICE);  Q [nx*nx], R [nu*nu]: shared (DEVICE)
+ *   maxiter 150 and eps 0.01 are the reference's constants (:77-78 / :87-88)
+ *   K [nu*nx][n] out (column-major nu x nx); X [nx*nx][n] out or NULL; iters [n] out or NULL */
+int crb_lqr_dlqr_batched(crb_ctx* ctx, int64_t n, int nx, int nu, const float* A, const float* B,
+                         const float* Q, const float* R, int maxiter, float eps, float* K, float* X,
+                         int32_t* iters);
 
 /* ---- summary statistics (the only inter-GPU payload) ------------------------------------------- */
 #define CRB_STATS_LEN 8

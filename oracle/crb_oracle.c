@@ -419,3 +419,89 @@ double crb_oracle_philox_uniform12(uint64_t seed, uint64_t index) {
   }
   return (double)(1.0f + (float)(c[0] >> 9) * 1.1920928955078125e-07f);
 }
+
+/* ---- solve_DARE() + dlqr(): src/lqr_steer_control.cpp:75-96 (nx = 4, nu = 1, scalar R) and
+ * src/lqr_speed_steer_control.cpp:85-106 (nx = 5, nu = 2, 2x2 R).  Column-major matrices.
+ *   Xn = A^T*X*A - A^T*X*B/(R + B^T*X*B) * B^T*X*A + Q        (:81 / :91, evaluated left to right)
+ *   stop when max|Xn - X| < eps (:83 / :93) and return Xn; after maxiter iterations return X (:89 / :99)
+ *   K  = 1.0/(B^T*X*B + R) * (B^T*X*A)                        (:94)   [nu = 1]
+ *   K  = (B^T*X*B + R).inverse() * (B^T*X*A)                  (:104)  [nu = 2]
+ * Plain binary32, separate multiply and add, sequential-k sums (see the file header). */
+static void mm_cm(const float* A, int ra, int ca, const float* B, int cb, float* C) {
+  matmul(A, ra, ca, B, cb, C, CRB_ORDER_SEQ);
+}
+int crb_oracle_dlqr(int nx, int nu, const float* A, const float* B, const float* Q, const float* R,
+                    int maxiter, float eps, float* K /*nu x nx*/, float* Xout /*nx x nx or NULL*/) {
+  float X[25], Xn[25], At[25], Bt[10], M1[25], T1[25], V1[10], V2[10], M2[25], M3[25], T2[25];
+  float BtX[10], S[4], Sinv[4];
+  const int nn = nx * nx;
+  transpose(A, nx, nx, At);
+  transpose(B, nx, nu, Bt);
+  for (int i = 0; i < nn; ++i) X[i] = Q[i];
+  int it = 0, converged = 0;
+  for (; it < maxiter; ++it) {
+    mm_cm(At, nx, nx, X, nx, M1);          /* A^T*X          */
+    mm_cm(M1, nx, nx, A, nx, T1);          /* (A^T*X)*A      */
+    mm_cm(M1, nx, nx, B, nu, V1);          /* (A^T*X)*B      */
+    mm_cm(Bt, nu, nx, X, nx, BtX);         /* B^T*X          */
+    mm_cm(BtX, nu, nx, B, nu, S);          /* (B^T*X)*B      */
+    if (nu == 1) {
+      const float s = R[0] + S[0];
+      for (int i = 0; i < nx; ++i) V2[i] = V1[i] / s;
+    } else {
+      for (int i = 0; i < 4; ++i) S[i] = R[i] + S[i];
+      const float det = S[0] * S[3] - S[1] * S[2];
+      const float invdet = 1.0f / det;
+      Sinv[0] = S[3] * invdet; Sinv[1] = -S[1] * invdet; Sinv[2] = -S[2] * invdet; Sinv[3] = S[0] * invdet;
+      mm_cm(V1, nx, 2, Sinv, 2, V2);
+    }
+    mm_cm(V2, nx, nu, Bt, nx, M2);         /* (...)*B^T      */
+    mm_cm(M2, nx, nx, X, nx, M3);          /* (...)*X        */
+    mm_cm(M3, nx, nx, A, nx, T2);          /* (...)*A        */
+    float maxerr = 0.0f;
+    for (int i = 0; i < nn; ++i) {
+      Xn[i] = (T1[i] - T2[i]) + Q[i];
+      const float e = fabsf(Xn[i] - X[i]);
+      if (i == 0 || e > maxerr) maxerr = e;
+    }
+    if (maxerr < eps) { for (int i = 0; i < nn; ++i) X[i] = Xn[i]; converged = 1; ++it; break; }
+    for (int i = 0; i < nn; ++i) X[i] = Xn[i];
+  }
+  (void)converged;
+  /* dlqr */
+  float BtXA[10];
+  mm_cm(Bt, nu, nx, X, nx, BtX);
+  mm_cm(BtX, nu, nx, B, nu, S);
+  mm_cm(BtX, nu, nx, A, nx, BtXA);
+  if (nu == 1) {
+    const float s2 = S[0] + R[0];
+    const float inv = (float)(1.0 / (double)s2);          /* double scalar converted to the matrix scalar */
+    for (int j = 0; j < nx; ++j) K[j] = inv * BtXA[j];
+  } else {
+    for (int i = 0; i < 4; ++i) S[i] = S[i] + R[i];
+    const float det = S[0] * S[3] - S[1] * S[2];
+    const float invdet = 1.0f / det;
+    Sinv[0] = S[3] * invdet; Sinv[1] = -S[1] * invdet; Sinv[2] = -S[2] * invdet; Sinv[3] = S[0] * invdet;
+    mm_cm(Sinv, 2, 2, BtXA, nx, K);
+  }
+  if (Xout) for (int i = 0; i < nn; ++i) Xout[i] = X[i];
+  return it;
+}
+
+void crb_oracle_dlqr_batched(int64_t n, int nx, int nu, const float* A, const float* B, const float* Q,
+                             const float* R, int maxiter, float eps, float* K, float* X, int32_t* iters,
+                             int nthreads) {
+#ifdef _OPENMP
+  if (nthreads <= 0) nthreads = omp_get_max_threads();
+#pragma omp parallel for num_threads(nthreads) schedule(dynamic, 256)
+#endif
+  for (int64_t i = 0; i < n; ++i) {
+    float a[25], b[10], k[10], x[25];
+    for (int f = 0; f < nx * nx; ++f) a[f] = A[(int64_t)f * n + i];
+    for (int f = 0; f < nx * nu; ++f) b[f] = B[(int64_t)f * n + i];
+    const int it = crb_oracle_dlqr(nx, nu, a, b, Q, R, maxiter, eps, k, x);
+    for (int f = 0; f < nu * nx; ++f) K[(int64_t)f * n + i] = k[f];
+    if (X) for (int f = 0; f < nx * nx; ++f) X[(int64_t)f * n + i] = x[f];
+    if (iters) iters[i] = it;
+  }
+}

@@ -61,6 +61,12 @@ void crb_oracle_pf_estimate(int64_t n, const float* px, float* pw, float xEst[4]
 int crb_oracle_pf_resample(int64_t n, float* px, float* pw, const double* uniforms, float nth,
                            int reference_mode, float* neff_out);
 double crb_oracle_philox_uniform12(uint64_t seed, uint64_t index);
+/* solve_DARE() + dlqr(): lqr_steer_control.cpp:75-96 / lqr_speed_steer_control.cpp:85-106 */
+int crb_oracle_dlqr(int nx, int nu, const float* A, const float* B, const float* Q, const float* R,
+                    int maxiter, float eps, float* K, float* Xout);
+void crb_oracle_dlqr_batched(int64_t n, int nx, int nu, const float* A, const float* B, const float* Q,
+                             const float* R, int maxiter, float eps, float* K, float* X, int32_t* iters,
+                             int nthreads);
 void crb_oracle_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 int crb_oracle_num_threads(void);
 /* verification aids for arithmetic shortcuts of the CUDA PF kernel (see crb_oracle.c) */

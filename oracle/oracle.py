@@ -162,6 +162,20 @@ def philox_uniform12(seed, index):
     return L.crb_oracle_philox_uniform12(int(seed), int(index))
 
 
+def dlqr_batched(A, B, Q, R, nx, nu, maxiter=150, eps=0.01, nthreads=0):
+    """A [nx*nx, n], B [nx*nu, n] column-major per agent; Q [nx*nx], R [nu*nu] shared.
+    Returns dict(K [nu*nx, n], X [nx*nx, n], iters [n])."""
+    L = lib()
+    L.crb_oracle_dlqr_batched.argtypes = [C.c_int64, C.c_int, C.c_int, f32p, f32p, f32p, f32p, C.c_int, C.c_float,
+                                          f32p, f32p, i32p, C.c_int]
+    A = np.ascontiguousarray(A, np.float32); B = np.ascontiguousarray(B, np.float32)
+    n = A.shape[1]
+    K = np.zeros((nu * nx, n), np.float32); X = np.zeros((nx * nx, n), np.float32); it = np.zeros(n, np.int32)
+    L.crb_oracle_dlqr_batched(n, nx, nu, A, B, np.ascontiguousarray(Q, np.float32).reshape(-1),
+                              np.ascontiguousarray(R, np.float32).reshape(-1), maxiter, eps, K, X, it, nthreads)
+    return dict(K=K, X=X, iters=it)
+
+
 def pf_estimate(px, pw):
     px = np.ascontiguousarray(px, np.float32)
     pw = np.ascontiguousarray(pw, np.float32).copy()

@@ -8,7 +8,8 @@ struct Point2i { int x, y; Point2i() : x(0), y(0) {} Point2i(int a, int b) : x(a
 struct Scalar { double v[4]; Scalar(double a = 0, double b = 0, double c = 0, double d = 0) { v[0] = a; v[1] = b; v[2] = c; v[3] = d; } };
 struct Size { int w, h; Size(double a, double b) : w((int)a), h((int)b) {} };
 struct Mat { int rows, cols; Mat() : rows(0), cols(0) {} Mat(int r, int c, int, Scalar = Scalar()) : rows(r), cols(c) {} };
-enum { CV_8UC3_ = 16, WINDOW_NORMAL = 0, MARKER_CROSS = 0 };
+enum { CV_8UC3_ = 16, WINDOW_NORMAL = 0, MARKER_CROSS = 0, FONT_HERSHEY_SIMPLEX = 0 };
+inline void putText(Mat, const std::string&, Point2i, int, double, Scalar, int = 1) {}
 inline void namedWindow(const std::string&, int = 0) {}
 inline void imshow(const std::string&, const Mat&) {}
 inline int waitKey(int = 0) { return 0; }

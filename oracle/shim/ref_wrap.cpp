@@ -108,5 +108,28 @@ void ref_fg_eval(const float* xref /*4xT col-major*/, const double* vars, double
   f(fgv, v);
   for (size_t i = 0; i < fgv.size(); ++i) fg[i] = CppAD::Value(fgv[i]);
 }
+#elif WHICH == 4
+// src/lqr_steer_control.cpp: solve_DARE :75-90, dlqr :92-96 (4 states, 1 input, scalar R)
+void ref_dlqr4(const float* A, const float* B, const float* Q, float R, float* K, float* X) {
+  Eigen::Matrix4f Am, Qm; Eigen::Vector4f Bm;
+  for (int i = 0; i < 16; ++i) { Am.d[i] = A[i]; Qm.d[i] = Q[i]; }
+  for (int i = 0; i < 4; ++i) Bm(i) = B[i];
+  Eigen::Matrix4f Xm = solve_DARE(Am, Bm, Qm, R);
+  Eigen::RowVector4f Km = dlqr(Am, Bm, Qm, R);
+  for (int i = 0; i < 4; ++i) K[i] = Km(i);
+  for (int i = 0; i < 16; ++i) X[i] = Xm.d[i];
+}
+#elif WHICH == 5
+// src/lqr_speed_steer_control.cpp: solve_DARE :85-100, dlqr :102-106 (5 states, 2 inputs)
+void ref_dlqr5(const float* A, const float* B, const float* Q, const float* R, float* K, float* X) {
+  Matrix5f Am, Qm; Matrix52f Bm; Eigen::Matrix2f Rm;
+  for (int i = 0; i < 25; ++i) { Am.d[i] = A[i]; Qm.d[i] = Q[i]; }
+  for (int i = 0; i < 10; ++i) Bm.d[i] = B[i];
+  for (int i = 0; i < 4; ++i) Rm.d[i] = R[i];
+  Matrix5f Xm = solve_DARE(Am, Bm, Qm, Rm);
+  Matrix25f Km = dlqr(Am, Bm, Qm, Rm);
+  for (int i = 0; i < 10; ++i) K[i] = Km.d[i];
+  for (int i = 0; i < 25; ++i) X[i] = Xm.d[i];
+}
 #endif
 }

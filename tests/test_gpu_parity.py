@@ -407,3 +407,19 @@ def test_pf_resample_matches_oracle(engine):
     pxd, pwd = _dev(px, pw)
     did, neff = engine.pf_resample(pxd, pwd, uniforms=None)
     assert not did and abs(neff - n) < 1e-3 * n and np.array_equal(pxd.cpu().numpy(), px)
+
+
+@pytest.mark.parametrize("nx,nu,n", [(4, 1, 1), (4, 1, 50_001), (5, 2, 20_003)])
+def test_dlqr_bit_exact_vs_oracle(engine, nx, nu, n):
+    """solve_DARE + dlqr (row f-4): no transcendental, so the GPU must match the oracle bit for bit,
+    iteration counts included."""
+    import torch
+    A, B, Q, R = synth.lqr_inputs(n, nx)
+    Ad, Bd, Qd, Rd = _dev(A, B, Q, R)
+    X = torch.empty((nx * nx, n), dtype=torch.float32, device="cuda")
+    it = torch.empty(n, dtype=torch.int32, device="cuda")
+    K = engine.dlqr(Ad, Bd, Qd, Rd, nx, nu, X=X, iters=it)
+    torch.cuda.synchronize()
+    r = O.dlqr_batched(A, B, Q, R, nx, nu)
+    assert np.array_equal(it.cpu().numpy(), r["iters"])
+    assert np.array_equal(K.cpu().numpy(), r["K"]) and np.array_equal(X.cpu().numpy(), r["X"])
