@@ -53,6 +53,15 @@ int crb_ctx_pipe_reserve(crb_ctx* ctx, int slot, size_t bytes);
 int crb_ctx_scratch_reserve(crb_ctx* ctx, size_t bytes);
 int crb_ctx_mpc_ws_reserve(crb_ctx* ctx, size_t bytes);
 
+// Strided host<->device block copy for the *_host pipelines.  Measured on this platform
+// (scripts/pcie_probe.py + bench e2e): plain 1-D copies reach 48 (H2D) / 57 (D2H) GB/s, one
+// cudaMemcpy2DAsync per array ~31 GB/s per direction in duplex, and splitting it into per-row 1-D copies is
+// SLOWER (enqueue-bound: 2.0-2.8e8 vs 3.45e8 EKF updates/s end to end), so the 2-D copy stays.
+static inline cudaError_t crb_copy_rows(void* dst, size_t dpitch, const void* src, size_t spitch,
+                                        size_t width, size_t rows, cudaMemcpyKind kind, cudaStream_t st) {
+  return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, kind, st);
+}
+
 static inline int crb_grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
 
 // Streaming (evict-first) global accesses for data that is touched exactly once per launch.

@@ -356,7 +356,13 @@ extern "C" int crb_ekf_step_batched_host(crb_ctx* ctx, int64_t n, float* x, floa
   if (n == 0) return CRB_OK;
   CRB_REQUIRE(x && P && z && u, "NULL array");
   CRB_CUDA(cudaSetDevice(ctx->device));
-  const int64_t chunk_cap = n < (int64_t)131072 ? n : (int64_t)131072;
+  static int64_t chunk_pref = 0;  // CRB_EKF_CHUNK overrides the staging chunk (agents) for A/B
+  if (chunk_pref == 0) {
+    const char* e = getenv("CRB_EKF_CHUNK");
+    chunk_pref = e ? atoll(e) : 131072;
+    if (chunk_pref < 1024) chunk_pref = 131072;
+  }
+  const int64_t chunk_cap = n < chunk_pref ? n : chunk_pref;
   const size_t nf = 20 + (size_t)4 * n_steps;  // x4 P16 z2s u2s
   const size_t pitch = (size_t)chunk_cap * sizeof(float);
   for (int s = 0; s < CRB_N_PIPE; ++s) {
@@ -373,16 +379,16 @@ extern "C" int crb_ekf_step_batched_host(crb_ctx* ctx, int64_t n, float* x, floa
     float* dz = dP + 16 * chunk_cap;
     float* du = dz + (size_t)2 * n_steps * chunk_cap;
     const size_t w = (size_t)cnt * sizeof(float);
-    CRB_CUDA(cudaMemcpy2DAsync(dx, pitch, x + i0, hp, w, 4, cudaMemcpyHostToDevice, st));
-    CRB_CUDA(cudaMemcpy2DAsync(dP, pitch, P + i0, hp, w, 16, cudaMemcpyHostToDevice, st));
-    CRB_CUDA(cudaMemcpy2DAsync(dz, pitch, z + i0, hp, w, (size_t)2 * n_steps,
+    CRB_CUDA(crb_copy_rows(dx, pitch, x + i0, hp, w, 4, cudaMemcpyHostToDevice, st));
+    CRB_CUDA(crb_copy_rows(dP, pitch, P + i0, hp, w, 16, cudaMemcpyHostToDevice, st));
+    CRB_CUDA(crb_copy_rows(dz, pitch, z + i0, hp, w, (size_t)2 * n_steps,
                                cudaMemcpyHostToDevice, st));
-    CRB_CUDA(cudaMemcpy2DAsync(du, pitch, u + i0, hp, w, (size_t)2 * n_steps,
+    CRB_CUDA(crb_copy_rows(du, pitch, u + i0, hp, w, (size_t)2 * n_steps,
                                cudaMemcpyHostToDevice, st));
     int rc = ekf_launch(ctx, st, cnt, chunk_cap, dx, dP, dz, du, chunk_cap, n_steps, prm);
     if (rc) return rc;
-    CRB_CUDA(cudaMemcpy2DAsync(x + i0, hp, dx, pitch, w, 4, cudaMemcpyDeviceToHost, st));
-    CRB_CUDA(cudaMemcpy2DAsync(P + i0, hp, dP, pitch, w, 16, cudaMemcpyDeviceToHost, st));
+    CRB_CUDA(crb_copy_rows(x + i0, hp, dx, pitch, w, 4, cudaMemcpyDeviceToHost, st));
+    CRB_CUDA(crb_copy_rows(P + i0, hp, dP, pitch, w, 16, cudaMemcpyDeviceToHost, st));
   }
   for (int s = 0; s < CRB_N_PIPE; ++s) CRB_CUDA(cudaStreamSynchronize(ctx->pipe_stream[s]));
   return CRB_OK;

@@ -851,19 +851,19 @@ extern "C" int crb_mpc_solve_batched_host(crb_ctx* ctx, int64_t n, int T, const 
     int32_t* dit = dstat + chunk_cap;
     float* scratch = (float*)(dit + chunk_cap);
     const size_t w = (size_t)cnt * sizeof(float);
-    CRB_CUDA(cudaMemcpy2DAsync(dx0, pitch, x0 + i0, hp, w, 4, cudaMemcpyHostToDevice, st));
-    CRB_CUDA(cudaMemcpy2DAsync(dxr, pitch, xref + i0, hp, w, (size_t)4 * T, cudaMemcpyHostToDevice,
+    CRB_CUDA(crb_copy_rows(dx0, pitch, x0 + i0, hp, w, 4, cudaMemcpyHostToDevice, st));
+    CRB_CUDA(crb_copy_rows(dxr, pitch, xref + i0, hp, w, (size_t)4 * T, cudaMemcpyHostToDevice,
                                st));
     if (u_init)
-      CRB_CUDA(cudaMemcpy2DAsync(dui, pitch, u_init + i0, hp, w, (size_t)2 * N,
+      CRB_CUDA(crb_copy_rows(dui, pitch, u_init + i0, hp, w, (size_t)2 * N,
                                  cudaMemcpyHostToDevice, st));
     rc = mpc_launch(ctx, st, cnt, chunk_cap, T, dx0, dxr, u_init ? dui : nullptr, scratch,
                     chunk_cap, sol ? dsol : nullptr, u0 ? du0 : nullptr, cost ? dcost : nullptr,
                     status ? dstat : nullptr, iters ? dit : nullptr, prm);
     if (rc) return rc;
     if (sol)
-      CRB_CUDA(cudaMemcpy2DAsync(sol + i0, hp, dsol, pitch, w, nsol, cudaMemcpyDeviceToHost, st));
-    if (u0) CRB_CUDA(cudaMemcpy2DAsync(u0 + i0, hp, du0, pitch, w, 2, cudaMemcpyDeviceToHost, st));
+      CRB_CUDA(crb_copy_rows(sol + i0, hp, dsol, pitch, w, nsol, cudaMemcpyDeviceToHost, st));
+    if (u0) CRB_CUDA(crb_copy_rows(u0 + i0, hp, du0, pitch, w, 2, cudaMemcpyDeviceToHost, st));
     if (cost) CRB_CUDA(cudaMemcpyAsync(cost + i0, dcost, w, cudaMemcpyDeviceToHost, st));
     if (status) CRB_CUDA(cudaMemcpyAsync(status + i0, dstat, w, cudaMemcpyDeviceToHost, st));
     if (iters) CRB_CUDA(cudaMemcpyAsync(iters + i0, dit, w, cudaMemcpyDeviceToHost, st));
