@@ -48,6 +48,15 @@ MPC_BYTES = 344 + 472 # read x0 4 + xref 80, write sol 118 + u0 2 (+cost,status,
 NSETS = 3
 
 
+def host_threads() -> int:
+    """All host cores this process may use.  torchrun exports OMP_NUM_THREADS=1, which would silently make the
+    CPU arm single-threaded; the oracle takes an explicit thread count instead."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -310,7 +319,7 @@ def cpu_ekf(host=None):
     n = EKF_N
     x, P, z, u = host if host is not None else synth.ekf_inputs(n)
     x, P = x.copy(), P.copy()
-    thr = O.num_threads()
+    thr = host_threads()
     v, calls, el = cpu_time(lambda: O.ekf_step_batched(x, P, z, u, nthreads=thr, inplace=True), n,
                             budget_s=5.0)
     return dict(value=v, unit="updates/s", cores=thr, kind="port",
@@ -366,7 +375,7 @@ def cpu_pf(host=None, lm=None):
     px, pw, noise = host if host is not None else synth.pf_inputs(n)
     lm = lm if lm is not None else synth.pf_landmarks(PF_LM)
     px, pw0 = px.copy(), pw.copy()
-    thr = O.num_threads()
+    thr = host_threads()
 
     def one():
         pw[:] = pw0          # keep the weights in the normal range across repeated steps
@@ -467,7 +476,7 @@ def cpu_mpc(st=None, xref=None, sample=8192):
         st, pind = synth.mpc_states(sample, course=course)
         xref, _ = synth.mpc_xref_numpy(st, pind, T, course=course)
     st, xref = np.ascontiguousarray(st[:, :sample]), np.ascontiguousarray(xref[:, :sample])
-    thr = O.num_threads()
+    thr = host_threads()
     prm = O.mpc_params(max_iter=MPC_ITER, du_th=MPC_DUTH, max_ls=MPC_LS)
     v, calls, el = cpu_time(lambda: O.mpc_solve_batched(st, xref, T, prm, nthreads=thr), sample,
                             budget_s=5.0)
@@ -476,6 +485,31 @@ def cpu_mpc(st=None, xref=None, sample=8192):
                        f"oracle/crb_oracle_mpc.c same algorithm, OpenMP {thr} threads, {el:.1f} s; "
                        "the reference's CppAD+IPOPT solve cannot be built here (its own budget is "
                        "50 ms per solve, model_predictive_control.cpp:328)")
+
+
+def bench_ekf_multistep(eng, rank, world, steps, warmup):
+    """Row f-3: 2^20 agents x 100 filter steps per launch, state kept in registers (SURVEY d-3 asks for it).
+    16 B/update of (z,u) traffic, so the kernel leaves the HBM roofline and becomes issue-bound."""
+    import torch
+    from cpprobotics_b200 import synth
+    n, ns = 1 << 20, 100
+    dev = torch.device("cuda", torch.cuda.current_device())
+    x, P, z, u = synth.ekf_inputs(n, i0=rank * n, n_steps=1)
+    xd, Pd = torch.from_numpy(x).to(dev), torch.from_numpy(P).to(dev)
+    g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
+    zd = xd[:2].repeat(ns, 1) + 0.5 * torch.randn((2 * ns, n), device=dev, generator=g)
+    ud = torch.tensor([1.0, 0.1], device=dev).repeat(ns).unsqueeze(1) + 0.1 * torch.randn((2 * ns, n), device=dev, generator=g)
+    zd, ud = zd.contiguous(), ud.contiguous()
+    ms, _ = time_device_steps(lambda k: eng.ekf_estimation(xd, Pd, zd, ud, n_steps=ns), steps, 2, world, eng=eng)
+    ok = bool(torch.isfinite(Pd).all().item())
+    return dict(metric="EKF updates/sec, 100 steps per launch (state resident in registers)",
+                value=world * n * ns * steps / (ms * 1e-3), unit="updates/s", ms_per_step=ms / steps,
+                config=dict(workload="ekf_2^20_agents_100_steps_per_launch", finite=ok),
+                roofline=dict(bound="hbm", achieved=(16.0 * ns + 160.0) * n * steps / (ms * 1e-3) / 1e9,
+                              peak=peaks()[0], unit="GB/s",
+                              frac=(16.0 * ns + 160.0) * n * steps / (ms * 1e-3) / 1e9 / peaks()[0], traffic=None,
+                              note="16 B/update + 160 B/agent once: far below the HBM roofline by design; the "
+                                   "limit here is instruction issue (~460 instructions per update)"))
 
 
 def bench_lqr(eng, rank, world, steps, warmup, with_cpu):
@@ -504,7 +538,7 @@ def bench_lqr(eng, rank, world, steps, warmup, with_cpu):
                              kernel="crb_lqr_dlqr_kernel<4,1>"))
     if with_cpu and rank == 0:
         from oracle import oracle as O
-        thr = O.num_threads()
+        thr = host_threads()
         m = 1 << 16
         v, calls, el = cpu_time(lambda: O.dlqr_batched(A[:, :m], B[:, :m], Q, R, nx, nu, nthreads=thr), m, budget_s=3.0)
         out["cpu_baseline"] = dict(value=v, unit="solves/s", cores=thr, kind="port",
@@ -534,6 +568,8 @@ def run_ours(args):
         head = bench_ekf(eng, rank, world, args.steps, args.warmup, with_cpu=not args.no_cpu)
         if args.workload in ("all", "pf"):
             res["pf"] = bench_pf(eng, rank, world, args.steps, args.warmup, with_cpu=not args.no_cpu)
+        if args.workload in ("all", "ekf100"):
+            res["ekf_100_steps"] = bench_ekf_multistep(eng, rank, world, 3, 2)
         if args.workload in ("all", "lqr"):
             res["lqr"] = bench_lqr(eng, rank, world, max(3, args.steps // 5), 3, with_cpu=not args.no_cpu)
         if args.workload in ("all", "mpc"):
@@ -574,7 +610,7 @@ def run_reference(args):
     from cpprobotics_b200 import synth
     n = EKF_N
     x, P, z, u = synth.ekf_inputs(n)
-    thr = O.num_threads()
+    thr = host_threads()
     for _ in range(args.warmup):
         O.ekf_step_batched(x, P, z, u, nthreads=thr, inplace=True)
     t0 = time.perf_counter()
@@ -607,7 +643,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="all", choices=["all", "ekf", "pf", "mpc", "lqr"])
+    ap.add_argument("--workload", default="all", choices=["all", "ekf", "ekf100", "pf", "mpc", "lqr"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
