@@ -827,7 +827,13 @@ extern "C" int crb_mpc_solve_batched_host(crb_ctx* ctx, int64_t n, int T, const 
   if (n == 0) return CRB_OK;
   CRB_CUDA(cudaSetDevice(ctx->device));
   const int N = T - 1;
-  const int64_t chunk_cap = n < (int64_t)32768 ? n : (int64_t)32768;
+  static int64_t chunk_pref = 0;  // CRB_MPC_CHUNK overrides the staging chunk (problems) for A/B
+  if (chunk_pref == 0) {
+    const char* e = getenv("CRB_MPC_CHUNK");
+    chunk_pref = e ? atoll(e) : 32768;
+    if (chunk_pref < 128) chunk_pref = 32768;
+  }
+  const int64_t chunk_cap = n < chunk_pref ? n : chunk_pref;
   const size_t nsol = (size_t)4 * T + 2 * N;
   // per slot: inputs (4 + 4T + 2N), outputs (nsol + 2 + 1 + 1 + 1), then the solver workspace
   const size_t nf = (size_t)4 + 4 * T + 2 * N + nsol + 5;
