@@ -356,6 +356,19 @@ extern "C" int crb_ekf_step_batched_host(crb_ctx* ctx, int64_t n, float* x, floa
   if (n == 0) return CRB_OK;
   CRB_REQUIRE(x && P && z && u, "NULL array");
   CRB_CUDA(cudaSetDevice(ctx->device));
+  // Pinned + mapped buffers: run the resident kernel on them directly (see crb_host_mapped).
+  if (crb_zero_copy_enabled()) {
+    float *mx, *mP;
+    const float *mz, *mu;
+    if (crb_host_mapped(x, &mx) && crb_host_mapped(P, &mP) && crb_host_mapped(z, &mz) &&
+        crb_host_mapped(u, &mu)) {
+      cudaStream_t st = ctx->pipe_stream[0];
+      int rc = ekf_launch(ctx, st, n, n, mx, mP, mz, mu, n, n_steps, prm);
+      if (rc) return rc;
+      CRB_CUDA(cudaStreamSynchronize(st));
+      return CRB_OK;
+    }
+  }
   static int64_t chunk_pref = 0;  // CRB_EKF_CHUNK overrides the staging chunk (agents) for A/B
   if (chunk_pref == 0) {
     const char* e = getenv("CRB_EKF_CHUNK");

@@ -830,8 +830,10 @@ extern "C" int crb_mpc_solve_batched_host(crb_ctx* ctx, int64_t n, int T, const 
   static int64_t chunk_pref = 0;  // CRB_MPC_CHUNK overrides the staging chunk (problems) for A/B
   if (chunk_pref == 0) {
     const char* e = getenv("CRB_MPC_CHUNK");
-    chunk_pref = e ? atoll(e) : 32768;
-    if (chunk_pref < 128) chunk_pref = 32768;
+    // 8192 problems x CRB_N_PIPE = 8 slots: every chunk is resident at once and the first solve starts
+    // after 1/8 of the upload (measured, pinned buffers: 44.5 M solves/s vs 41.8 at 32768, 40.5 at 4096)
+    chunk_pref = e ? atoll(e) : 8192;
+    if (chunk_pref < 128) chunk_pref = 8192;
   }
   const int64_t chunk_cap = n < chunk_pref ? n : chunk_pref;
   const size_t nsol = (size_t)4 * T + 2 * N;
@@ -843,6 +845,15 @@ extern "C" int crb_mpc_solve_batched_host(crb_ctx* ctx, int64_t n, int T, const 
     if (rc) return rc;
   }
   const size_t hp = (size_t)n * sizeof(float);
+  // Outputs in pinned + mapped memory are written by the kernel itself (see crb_host_mapped): problems
+  // finish at different times, so the stores trickle over PCIe underneath the solve instead of queueing
+  // as D2H copies behind it.  Inputs stay on the copy engine: a kernel that reads them over PCIe stalls
+  // its whole (single) wave on the link first (measured: 34.7 M solves/s fully zero-copy vs 37.2 staged).
+  float *msol = nullptr, *mu0 = nullptr, *mcost = nullptr;
+  int32_t *mstat = nullptr, *mit = nullptr;
+  const bool direct_out = crb_zero_copy_enabled() && crb_host_mapped(sol, &msol) &&
+                          crb_host_mapped(u0, &mu0) && crb_host_mapped(cost, &mcost) &&
+                          crb_host_mapped(status, &mstat) && crb_host_mapped(iters, &mit);
   int slot = 0;
   for (int64_t i0 = 0; i0 < n; i0 += chunk_cap, slot = (slot + 1) % CRB_N_PIPE) {
     const int64_t cnt = (n - i0) < chunk_cap ? (n - i0) : chunk_cap;
@@ -863,6 +874,13 @@ extern "C" int crb_mpc_solve_batched_host(crb_ctx* ctx, int64_t n, int T, const 
     if (u_init)
       CRB_CUDA(crb_copy_rows(dui, pitch, u_init + i0, hp, w, (size_t)2 * N,
                                  cudaMemcpyHostToDevice, st));
+    if (direct_out) {  // results stored straight into the caller's pinned arrays (leading dimension n)
+      rc = mpc_launch(ctx, st, cnt, chunk_cap, T, dx0, dxr, u_init ? dui : nullptr, scratch, n,
+                      sol ? msol + i0 : nullptr, u0 ? mu0 + i0 : nullptr, cost ? mcost + i0 : nullptr,
+                      status ? mstat + i0 : nullptr, iters ? mit + i0 : nullptr, prm);
+      if (rc) return rc;
+      continue;
+    }
     rc = mpc_launch(ctx, st, cnt, chunk_cap, T, dx0, dxr, u_init ? dui : nullptr, scratch,
                     chunk_cap, sol ? dsol : nullptr, u0 ? du0 : nullptr, cost ? dcost : nullptr,
                     status ? dstat : nullptr, iters ? dit : nullptr, prm);

@@ -423,3 +423,81 @@ def test_dlqr_bit_exact_vs_oracle(engine, nx, nu, n):
     r = O.dlqr_batched(A, B, Q, R, nx, nu)
     assert np.array_equal(it.cpu().numpy(), r["iters"])
     assert np.array_equal(K.cpu().numpy(), r["K"]) and np.array_equal(X.cpu().numpy(), r["X"])
+
+
+# ---- *_host entries on pinned, device-mapped buffers (zero-copy path) ---------------------------------------
+def _pin(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+
+
+def test_host_entries_on_pinned_buffers_match_the_staged_pipeline_bitwise(engine):
+    """The *_host entries launch the resident kernels straight on pinned + mapped host memory (EKF, PF) or
+    let the solver store its results there (MPC); pageable numpy arrays take the staged pipeline.  Both
+    must give the same bits, including a ragged tail and odd leading dimensions."""
+    import torch
+    l0 = engine.launches
+    n = 300_001
+    x, P, z, u = synth.ekf_inputs(n, n_steps=2)
+    xs, Ps = x.copy(), P.copy()
+    engine.ekf_estimation_host(xs, Ps, z, u, n_steps=2)                 # pageable -> staged
+    staged_launches = engine.launches - l0
+    xp, Pp, zp, up = _pin(x), _pin(P), _pin(z), _pin(u)
+    l0 = engine.launches
+    engine.ekf_estimation_host(xp, Pp, zp, up, n_steps=2)               # pinned -> one direct launch
+    assert engine.launches - l0 == 1 and staged_launches >= 3
+    assert np.array_equal(xp.numpy(), xs) and np.array_equal(Pp.numpy(), Ps)
+
+    px, pw, noise = synth.pf_inputs(n)
+    lm = synth.pf_landmarks(8)
+    pxs, pws = px.copy(), pw.copy()
+    engine.pf_predict_weight_host(pxs, pws, noise, lm)
+    pxp, pwp, nop = _pin(px), _pin(pw), _pin(noise)
+    l0 = engine.launches
+    engine.pf_predict_weight_host(pxp, pwp, nop, lm)
+    assert engine.launches - l0 == 1
+    assert np.array_equal(pxp.numpy(), pxs) and np.array_equal(pwp.numpy(), pws)
+    # Philox mode (no noise array) through the same path
+    pxs2, pws2 = px.copy(), pw.copy()
+    engine.pf_predict_weight_host(pxs2, pws2, None, lm, seed=99)
+    pxp2, pwp2 = _pin(px), _pin(pw)
+    engine.pf_predict_weight_host(pxp2, pwp2, None, lm, seed=99)
+    assert np.array_equal(pxp2.numpy(), pxs2) and np.array_equal(pwp2.numpy(), pws2)
+
+    m, T = 70_001, 20
+    st, xref = _mpc_case(m, T)
+    prm = _params(max_iter=50, du_th=1e-4, max_ls=8)
+    a = _mpc_gpu(engine, st, xref, T, prm, host=True)                   # pageable outputs -> D2H copies
+    nsol = 4 * T + 2 * (T - 1)
+    out = dict(sol=torch.empty((nsol, m), dtype=torch.float32).pin_memory(),
+               u0=torch.empty((2, m), dtype=torch.float32).pin_memory(),
+               cost=torch.empty(m, dtype=torch.float32).pin_memory(),
+               status=torch.empty(m, dtype=torch.int32).pin_memory(),
+               iters=torch.empty(m, dtype=torch.int32).pin_memory())
+    engine.mpc_solve_host(_pin(st), _pin(xref), T, prm, **out)          # kernel stores into pinned memory
+    for k in ("status", "iters", "u0", "cost", "sol"):
+        assert np.array_equal(a[k], out[k].numpy()), k
+
+
+def test_host_zero_copy_can_be_switched_off(tmp_path):
+    """CRB_HOST_ZEROCOPY=0 forces the staged pipeline even for pinned buffers (fresh process: the switch
+    is read once)."""
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np, torch\n"
+        "from cpprobotics_b200 import synth\n"
+        "from cpprobotics_b200.engine import Engine\n"
+        "e = Engine(); n = 300001\n"
+        "x, P, z, u = (torch.from_numpy(a).pin_memory() for a in synth.ekf_inputs(n))\n"
+        "l0 = e.launches; e.ekf_estimation_host(x, P, z, u); print('LAUNCHES', e.launches - l0)\n"
+        "print('SUM', float(x.double().sum()))\n")
+    res = {}
+    for flag in ("0", "1"):
+        env = dict(os.environ, CRB_HOST_ZEROCOPY=flag,
+                   PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        res[flag] = dict(l.split() for l in r.stdout.strip().splitlines() if l.split()[0] in ("LAUNCHES", "SUM"))
+    assert int(res["1"]["LAUNCHES"]) == 1 and int(res["0"]["LAUNCHES"]) == 3
+    assert res["0"]["SUM"] == res["1"]["SUM"]
