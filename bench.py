@@ -37,8 +37,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 EKF_N = 1 << 20
-PF_N = 1 << 20
-PF_LM = 8
+PF_N = int(os.environ.get("CRB_BENCH_PF_N", 1 << 20))     # diagnostics only: the contract workload is 2^20 x 8
+PF_LM = int(os.environ.get("CRB_BENCH_PF_LM", 8))
 MPC_N = 1 << 16
 MPC_T = 20
 MPC_ITER, MPC_DUTH, MPC_LS = 50, 1e-4, 4   # IPOPT's max_iter (:326); tight du so the NLP converges
