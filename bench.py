@@ -319,6 +319,7 @@ def bench_ekf(eng, rank, world, steps, warmup, with_cpu):
     ms_k, _ = time_device_steps(step, steps, 3, world, eng=eng)
     peak, peak_src, _ = peaks()
     achieved = EKF_BYTES * n * steps / (ms_k * 1e-3) / 1e9
+    copy_gbs = copy_ceiling_gbs()
     # e2e through the host-pointer C-ABI entry: pinned host buffers, H2D + kernel + D2H every step
     hx, hP, hz, hu = (pinned(a) for a in host)
     ms_e = time_host_steps(lambda k: eng.ekf_estimation_host(hx, hP, hz, hu), max(3, min(steps, 10)),
@@ -328,9 +329,12 @@ def bench_ekf(eng, rank, world, steps, warmup, with_cpu):
                roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s",
                              frac=achieved / peak, traffic=traffic_for("ekf"), peak_source=peak_src,
                              kernel="crb_ekf_step_kernel",
-                             algorithmic_bytes_per_launch=EKF_BYTES * n),
+                             algorithmic_bytes_per_launch=EKF_BYTES * n,
+                             copy_gbs_same_run=copy_gbs, frac_of_copy_same_run=achieved / copy_gbs),
                e2e=dict(value=world * n * e_steps / (ms_e * 1e-3), unit="updates/s",
-                        h2d_bytes_per_step=96 * n, d2h_bytes_per_step=80 * n))
+                        h2d_bytes_per_step=96 * n, d2h_bytes_per_step=80 * n,
+                        path="crb_ekf_step_batched_host on pinned buffers: kernel reads/writes host memory "
+                             "over PCIe directly (zero-copy), synchronous per step"))
     if with_cpu and rank == 0:
         out["cpu_baseline"] = cpu_ekf(host)
     return out
@@ -345,7 +349,10 @@ def cpu_ekf(host=None):
     thr, mask = tuned_threads(lambda c: O.ekf_step_batched(x, P, z, u, nthreads=c, inplace=True))
     v, calls, el = cpu_time(lambda: O.ekf_step_batched(x, P, z, u, nthreads=thr, inplace=True), n,
                             budget_s=5.0)
-    return dict(value=v, unit="updates/s", cores=thr, kind="port",
+    m = 1 << 18                                   # SURVEY d-7: the same code on ONE core
+    x1, P1, z1, u1 = (np.ascontiguousarray(a[:, :m]) for a in (x, P, z, u))
+    v1, _, _ = cpu_time(lambda: O.ekf_step_batched(x1, P1, z1, u1, nthreads=1, inplace=True), m, budget_s=1.0)
+    return dict(value=v, unit="updates/s", cores=thr, kind="port", single_core_value=v1,
                 sample=f"{calls} x {n} agents x 1 step, oracle/crb_oracle.c -O2 -ffp-contract=off, "
                        f"OpenMP {thr} threads (fastest of 1/4..1 x the {mask}-cpu mask), {el:.1f} s")
 
@@ -382,7 +389,7 @@ def bench_pf(eng, rank, world, steps, warmup, with_cpu):
                            l2=f"{len(sets)} rotating buffer sets, {len(sets) * 29} MB > 126 MB L2"),
                roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s",
                              frac=achieved / peak, traffic=traffic_for("pf"), peak_source=peak_src,
-                             kernel="crb_pf_predict_weight_kernel",
+                             kernel="crb_pf_predict_weight_lean_kernel",
                              algorithmic_bytes_per_launch=PF_BYTES * n),
                e2e=dict(value=world * n * e_steps / (ms_e * 1e-3), unit="particles/s",
                         h2d_bytes_per_step=28 * n, d2h_bytes_per_step=20 * n))
@@ -503,7 +510,9 @@ def cpu_mpc(st=None, xref=None, sample=8192):
     thr, mask = tuned_threads(lambda c: O.mpc_solve_batched(st, xref, T, prm, nthreads=c))
     v, calls, el = cpu_time(lambda: O.mpc_solve_batched(st, xref, T, prm, nthreads=thr), sample,
                             budget_s=5.0)
-    return dict(value=v, unit="solves/s", cores=thr, kind="port",
+    st1, xr1 = np.ascontiguousarray(st[:, :256]), np.ascontiguousarray(xref[:, :256])
+    v1, _, _ = cpu_time(lambda: O.mpc_solve_batched(st1, xr1, T, prm, nthreads=1), 256, budget_s=1.0)
+    return dict(value=v, unit="solves/s", cores=thr, kind="port", single_core_value=v1,
                 sample=f"{calls} x {sample} agents (first {sample} of the GPU batch), T={T}, "
                        f"oracle/crb_oracle_mpc.c same algorithm, OpenMP {thr} threads (fastest of 1/4..1 x the "
                        f"{mask}-cpu mask), {el:.1f} s; "
@@ -534,6 +543,46 @@ def bench_ekf_multistep(eng, rank, world, steps, warmup):
                               frac=(16.0 * ns + 160.0) * n * steps / (ms * 1e-3) / 1e9 / peaks()[0], traffic=None,
                               note="16 B/update + 160 B/agent once: far below the HBM roofline by design; the "
                                    "limit here is instruction issue (~460 instructions per update)"))
+
+
+def copy_ceiling_gbs(nbytes=1 << 30, reps=10):
+    """Same-run device copy ceiling (SURVEY d-3): read + write bytes of a 1 GiB torch copy per second."""
+    import torch
+    src = torch.empty(nbytes // 4, dtype=torch.float32, device="cuda").fill_(1.0)
+    dst = torch.empty_like(src)
+    for _ in range(3):
+        dst.copy_(src)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        dst.copy_(src)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    del src, dst
+    return 2.0 * nbytes * reps / (ms * 1e-3) / 1e9
+
+
+def bench_ekf_large(eng, rank, world, steps, warmup):
+    """SURVEY d-3 also asks for 16 M agents: the same kernel where the per-launch fixed cost (~1.5 us) is
+    amortised over 3.1 GB of traffic."""
+    import torch
+    from cpprobotics_b200 import synth
+    n = 1 << 24
+    dev = torch.device("cuda", torch.cuda.current_device())
+    x, P, z, u = (torch.from_numpy(a).to(dev) for a in synth.ekf_inputs(1 << 20, i0=rank * n))
+    x, P, z, u = (t.repeat(1, 16).contiguous() for t in (x, P, z, u))       # 16 copies of the 2^20 block
+    def step(k):
+        eng.ekf_estimation(x, P, z, u)
+    ms, _ = time_device_steps(step, steps, warmup, world, eng=eng)
+    gbs = EKF_BYTES * n * steps / (ms * 1e-3) / 1e9
+    return dict(metric="EKF updates/sec, 2^24 agents x 1 step", value=world * n * steps / (ms * 1e-3),
+                unit="updates/s", ms_per_step=ms / steps,
+                config=dict(workload="ekf_2^24_agents_1_step_per_gpu", l2="3.1 GB per launch >> 126 MB L2"),
+                roofline=dict(bound="hbm", achieved=gbs, peak=peaks()[0], unit="GB/s", frac=gbs / peaks()[0],
+                              traffic=None, kernel="crb_ekf_step_kernel",
+                              algorithmic_bytes_per_launch=EKF_BYTES * n))
 
 
 def bench_lqr(eng, rank, world, steps, warmup, with_cpu):
@@ -595,6 +644,8 @@ def run_ours(args):
             res["pf"] = bench_pf(eng, rank, world, args.steps, args.warmup, with_cpu=not args.no_cpu)
         if args.workload in ("all", "ekf100"):
             res["ekf_100_steps"] = bench_ekf_multistep(eng, rank, world, 3, 2)
+        if args.workload in ("all", "ekf16m"):
+            res["ekf_16M_agents"] = bench_ekf_large(eng, rank, world, 5, 3)
         if args.workload in ("all", "lqr"):
             res["lqr"] = bench_lqr(eng, rank, world, max(3, args.steps // 5), 3, with_cpu=not args.no_cpu)
         if args.workload in ("all", "mpc"):
@@ -669,7 +720,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="all", choices=["all", "ekf", "ekf100", "pf", "mpc", "lqr"])
+    ap.add_argument("--workload", default="all", choices=["all", "ekf", "ekf100", "ekf16m", "pf", "mpc", "lqr"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
