@@ -93,6 +93,40 @@ static inline bool crb_host_mapped(T* host, T** dev) {
   return true;
 }
 
+// Programmatic dependent launch (PDL): back-to-back launches of the short streaming kernels (EKF step 30 us,
+// PF step 11 us) otherwise pay ~1.5 us each for the drain of kernel N plus the launch and prologue of
+// kernel N+1.  With the launch attribute below, kernel N+1's CTAs are scheduled as soon as every CTA of
+// kernel N has executed crb_pdl_launch_dependents() (or exited); they run their address arithmetic and
+// then block in crb_pdl_wait() until kernel N has completed and its writes are visible, so a truly
+// dependent sequence (EKF step k+1 reading step k's state) stays correct.  Both instructions are no-ops in
+// a kernel launched without the attribute.  CRB_PDL=0 disables the attribute (A/B).
+__device__ __forceinline__ void crb_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void crb_pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+static inline bool crb_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("CRB_PDL");
+    on = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return on != 0;
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t crb_launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block,
+                                         cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = crb_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline int crb_grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
 
 // Streaming (evict-first) global accesses for data that is touched exactly once per launch.

@@ -107,6 +107,8 @@ crb_ekf_step_kernel(int64_t count, int64_t ld, float* __restrict__ x, float* __r
                     int n_steps, EkfArgs a) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
+  crb_pdl_launch_dependents();   // the next launch may start scheduling its CTAs behind ours
+  crb_pdl_wait();   // the previous launch on this stream (e.g. the preceding filter step) is complete
   float xs[4], Ps[16];
 #pragma unroll
   for (int f = 0; f < 4; ++f) xs[f] = ld_stream(x + f * ld + i);
@@ -327,8 +329,8 @@ static int ekf_launch(crb_ctx* ctx, cudaStream_t st, int64_t count, int64_t ld, 
                                                                             ld_zu, n_steps, a);
       break;
     default:
-      crb_ekf_step_kernel<256, 4><<<crb_grid_for(count, 256), 256, 0, st>>>(count, ld, x, P, z, u,
-                                                                            ld_zu, n_steps, a);
+      CRB_CUDA(crb_launch_pdl(crb_ekf_step_kernel<256, 4>, (unsigned)crb_grid_for(count, 256), 256u, st,
+                              count, ld, x, P, z, u, ld_zu, n_steps, a));
   }
   CRB_CUDA(cudaGetLastError());
   ctx->launches++;

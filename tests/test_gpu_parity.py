@@ -537,3 +537,65 @@ def test_host_zero_copy_can_be_switched_off(tmp_path):
         res[flag] = dict(l.split() for l in r.stdout.strip().splitlines() if l.split()[0] in ("LAUNCHES", "SUM"))
     assert int(res["1"]["LAUNCHES"]) == 1 and int(res["0"]["LAUNCHES"]) == 3
     assert res["0"]["SUM"] == res["1"]["SUM"]
+
+
+# ---- BASELINE.json full sizes ----------------------------------------------------------------------------
+def test_full_size_ekf_2pow20_matches_oracle_and_is_shard_invariant(engine):
+    """configs[1] at full size: every agent against the oracle (field-normalised 1e-5), and the same bits
+    whether the batch runs as one launch or as two shards with an odd split (what a 2-GPU run does)."""
+    import torch
+    n = 1 << 20
+    x, P, z, u = synth.ekf_inputs(n)
+    xd, Pd, zd, ud = _dev(x, P, z, u)
+    engine.ekf_estimation(xd, Pd, zd, ud)
+    torch.cuda.synchronize()
+    xo, Po = O.ekf_step_batched(x, P, z, u)
+    assert field_err(xd.cpu().numpy(), xo) <= 1e-5 and field_err(Pd.cpu().numpy(), Po) <= 1e-5
+    k = 524_289
+    parts = []
+    for sl in (slice(0, k), slice(k, n)):
+        a = _dev(*(np.ascontiguousarray(t[:, sl]) for t in (x, P, z, u)))
+        engine.ekf_estimation(*a)
+        torch.cuda.synchronize()
+        parts.append((a[0].cpu().numpy(), a[1].cpu().numpy()))
+    assert np.array_equal(np.concatenate([p[0] for p in parts], axis=1), xd.cpu().numpy())
+    assert np.array_equal(np.concatenate([p[1] for p in parts], axis=1), Pd.cpu().numpy())
+
+
+def test_full_size_pf_2pow20_matches_oracle_and_is_shard_invariant(engine):
+    """configs[2] at full size (2^20 particles, 8 landmarks): positions and weights against the oracle, same
+    bits in two shards (even split: packed kernel; the shards' Philox/noise indices are absolute)."""
+    import torch
+    n = 1 << 20
+    px, pw, noise = synth.pf_inputs(n)
+    lm = synth.pf_landmarks(8)
+    pxd, pwd, nd = _dev(px, pw, noise)
+    engine.pf_predict_weight(pxd, pwd, nd, lm)
+    torch.cuda.synchronize()
+    pxo, pwo = O.pf_predict_weight_batched(px, pw, noise, lm)
+    assert np.abs(pxd.cpu().numpy() - pxo).max() <= 1e-5 * max(1.0, np.abs(pxo).max())
+    _assert_weights_close(pwd.cpu().numpy(), pwo, pxo, lm)
+    k = 1 << 19
+    outs = []
+    for sl in (slice(0, k), slice(k, n)):
+        a = _dev(np.ascontiguousarray(px[:, sl]), np.ascontiguousarray(pw[sl]), np.ascontiguousarray(noise[:, sl]))
+        engine.pf_predict_weight(a[0], a[1], a[2], lm)
+        torch.cuda.synchronize()
+        outs.append((a[0].cpu().numpy(), a[1].cpu().numpy()))
+    assert np.array_equal(np.concatenate([o[0] for o in outs], axis=1), pxd.cpu().numpy())
+    assert np.array_equal(np.concatenate([o[1] for o in outs]), pwd.cpu().numpy())
+    # the normalised weights still sum to one and the estimate is finite (size-independent property)
+    xe, Pe, sw = engine.pf_estimate(pxd, pwd)
+    assert np.isfinite(xe).all() and np.isfinite(Pe).all() and abs(float(pwd.double().sum().item()) - 1.0) < 1e-6
+
+
+def test_full_size_mpc_65536_bit_exact_vs_oracle(engine):
+    """configs[3] at full size: all 65 536 problems, every output word identical to the oracle."""
+    n, T = 1 << 16, 20
+    st, xref = _mpc_case(n, T)
+    prm = _params()
+    got = _mpc_gpu(engine, st, xref, T, prm)
+    want = O.mpc_solve_batched(st, xref, T, O.mpc_params())
+    for k in ("status", "iters", "u0", "cost", "sol"):
+        assert np.array_equal(got[k], want[k]), k
+    assert (got["status"] == 0).mean() > 0.999
