@@ -202,6 +202,12 @@ __device__ __forceinline__ void box_qp2(float Q00, float Q01, float Q11, float g
 // subtracted on the fly), gains out G [14(T-1)][n].
 // X [4T], U [2(T-1)] (item 2t+c, c = 0 delta, 1 a), XR [4T] (reference, already translated by
 // (ox, oy)), gains out G [14(T-1)]: thread pointers into the CTA-interleaved workspace, item stride LS.
+// L2 prefetch of one workspace word's 128-byte line (the warp's 32 lanes share it): no register, no wait.
+__device__ __forceinline__ void pf_l2(const float* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+template <int PFD>
 __device__ __forceinline__ void backward_sweep(int T, const float* __restrict__ X,
                                                const float* __restrict__ U,
                                                const float* __restrict__ XR, const MpcP& p,
@@ -251,6 +257,12 @@ __device__ __forceinline__ void backward_sweep(int T, const float* __restrict__ 
     float xt_n[4] = {0.0f, 0.0f, 0.0f, 0.0f}, xr_n[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     float um_n[2] = {0.0f, 0.0f};
     if (t >= 1) load_stage(t - 1, xt_n, xr_n, um_n);
+    if (PFD > 0 && t - 1 - PFD >= 0) {   // stage t-1-PFD: pull its lines into L2 now
+      const int tp = t - 1 - PFD;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { pf_l2(X + (tp * 4 + k) * LS); pf_l2(XR + (tp * 4 + k) * LS); }
+      if (tp >= 1) { pf_l2(U + ((tp - 1) * 2 + 0) * LS); pf_l2(U + ((tp - 1) * 2 + 1) * LS); }
+    }
     const float v = xt[3];
     float s, c, sd, cd;
     crb_sincosf(xt[2], s, c);
@@ -478,6 +490,7 @@ __device__ __forceinline__ void backward_sweep(int T, const float* __restrict__ 
 }
 
 // ---- forward sweep: clamped roll-out under the affine policy; returns dJ and sum|du| ----------------
+template <int PFD>
 __device__ __forceinline__ void forward_sweep(int T, float yaw0, float v0,
                                               const float* __restrict__ X,
                                               const float* __restrict__ U,
@@ -516,6 +529,15 @@ __device__ __forceinline__ void forward_sweep(int T, float yaw0, float v0,
 #pragma unroll
     for (int j = 0; j < NGAIN; ++j) gk_n[j] = 0.0f;
     if (t + 1 < T - 1) load_stage(t + 1, uo_n, gk_n, xo1_n, xr1_n);
+    if (PFD > 0 && t + 1 + PFD < T - 1) {   // stage t+1+PFD: pull its lines into L2 now
+      const int tp = t + 1 + PFD;
+      pf_l2(U + (tp * 2 + 0) * LS);
+      pf_l2(U + (tp * 2 + 1) * LS);
+#pragma unroll
+      for (int j = 0; j < NGAIN; ++j) pf_l2(G + (tp * NGAIN + j) * LS);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { pf_l2(X + ((tp + 1) * 4 + k) * LS); pf_l2(XR + ((tp + 1) * 4 + k) * LS); }
+    }
     float dx[4], dw[2] = {0.0f, 0.0f};
 #pragma unroll
     for (int k = 0; k < 4; ++k) dx[k] = xn[k] - xo[k];
@@ -601,6 +623,7 @@ __device__ __forceinline__ float direct_cost(int T, const float* __restrict__ X,
 // Workspace items per problem: XA [4T] XB [4T] UA [2N] UB [2N] G [14N] XR [4T]
 __host__ __device__ inline int mpc_ws_items(int T) { return 12 * T + (4 + NGAIN) * (T - 1); }
 
+template <int PFD>
 __global__ void __launch_bounds__(MPC_BLOCK, 4)
 crb_mpc_solve_kernel(int64_t count, int64_t ld_in, int T, const float* __restrict__ x0,
                      const float* __restrict__ xref, const float* __restrict__ u_init,
@@ -657,13 +680,13 @@ crb_mpc_solve_kernel(int64_t count, int64_t ld_in, int T, const float* __restric
     bool gn = false;  // Newton sweep; Gauss-Newton retry after a failed line search
     float Jc = J0;    // running cost
     while (it_count < p.max_iter) {
-      backward_sweep(T, X, U, XR, p, gn, G);
+      backward_sweep<PFD>(T, X, U, XR, p, gn, G);
       ++it_count;
       bool accepted = false, tiny = false;
       int jacc = 0;
       float dJ = 0.0f, du = 0.0f, alpha = 1.0f;
       for (int j = 0; j <= p.max_ls; ++j) {
-        forward_sweep(T, yaw0, v0, X, U, XR, G, alpha, p, Xn, Un, dJ, du);
+        forward_sweep<PFD>(T, yaw0, v0, X, U, XR, G, alpha, p, Xn, Un, dJ, du);
         if (j == 0) tiny = (du <= p.du_th) || (fabsf(dJ) <= p.j_tol * fabsf(Jc));
         if (dJ < 0.0f) { accepted = true; jacc = j; break; }
         if (tiny) break;
@@ -767,7 +790,7 @@ static int mpc_launch(crb_ctx* ctx, cudaStream_t st, int64_t count, int64_t ld, 
     const int k = e ? atoi(e) : 0;
     smem_cap = (k >= 1 && k <= 3) ? (int)((227 * 1024) / k - 2048) : 0;
     if (smem_cap > 0)
-      cudaFuncSetAttribute(crb_mpc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap);
+      cudaFuncSetAttribute(crb_mpc_solve_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap);
   }
   cfg.dynamicSmemBytes = (size_t)smem_cap;
   cudaLaunchAttribute attr[1];
@@ -786,8 +809,28 @@ static int mpc_launch(crb_ctx* ctx, cudaStream_t st, int64_t count, int64_t ld, 
   }
   cfg.attrs = attr;
   cfg.numAttrs = nattr;
-  CRB_CUDA(cudaLaunchKernelEx(&cfg, crb_mpc_solve_kernel, count, ld, T, x0, xref, u_init, scratch,
-                              ld_out, sol, u0, cost, status, iters, p));
+  static int pfd = -1;   // CRB_MPC_PREFETCH = L2 prefetch distance in stages (0 off, 2, 3, 4)
+  if (pfd < 0) {
+    const char* e = getenv("CRB_MPC_PREFETCH");
+    pfd = e ? atoi(e) : 0;
+  }
+  switch (pfd) {
+    case 2:
+      CRB_CUDA(cudaLaunchKernelEx(&cfg, crb_mpc_solve_kernel<2>, count, ld, T, x0, xref, u_init, scratch,
+                                  ld_out, sol, u0, cost, status, iters, p));
+      break;
+    case 3:
+      CRB_CUDA(cudaLaunchKernelEx(&cfg, crb_mpc_solve_kernel<3>, count, ld, T, x0, xref, u_init, scratch,
+                                  ld_out, sol, u0, cost, status, iters, p));
+      break;
+    case 4:
+      CRB_CUDA(cudaLaunchKernelEx(&cfg, crb_mpc_solve_kernel<4>, count, ld, T, x0, xref, u_init, scratch,
+                                  ld_out, sol, u0, cost, status, iters, p));
+      break;
+    default:
+      CRB_CUDA(cudaLaunchKernelEx(&cfg, crb_mpc_solve_kernel<0>, count, ld, T, x0, xref, u_init, scratch,
+                                  ld_out, sol, u0, cost, status, iters, p));
+  }
   CRB_CUDA(cudaGetLastError());
   ctx->launches++;
   return CRB_OK;
