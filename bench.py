@@ -398,6 +398,42 @@ def bench_pf(eng, rank, world, steps, warmup, with_cpu):
     return out
 
 
+def bench_pf_iteration(eng, rank, world, steps, warmup):
+    """Row f-2: one complete filter iteration per step = predict+weight (:81-102), normalise + estimate +
+    covariance (:104-107, host-visible results => one sync per step) and low-variance resampling
+    (:111-148, forced every step with nth = n).  Not graph-captured (the estimate returns to the host)."""
+    import torch
+    from cpprobotics_b200 import synth
+    n = 1 << 20
+    dev = torch.device("cuda", torch.cuda.current_device())
+    px, pw, noise = (torch.from_numpy(a).to(dev) for a in synth.pf_inputs(n, i0=rank * n, n_total=world * n))
+    lm = synth.pf_landmarks(PF_LM)
+    tmp = torch.empty_like(px)
+    st = {"resampled": 0}
+
+    def step(k):
+        eng.pf_predict_weight(px, pw, noise, lm)
+        eng.pf_estimate(px, pw)
+        did, _ = eng.pf_resample(px, pw, seed=k, nth=float(n), px_tmp=tmp)
+        st["resampled"] += int(did)
+    for k in range(warmup):
+        step(k)
+    barrier_sync(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    eng.bind_current_stream()
+    e0.record()
+    for k in range(steps):
+        step(warmup + k)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = max_over_ranks(e0.elapsed_time(e1), world)
+    return dict(metric="PF filter iterations (predict+weight, estimate, resample) x particles per second",
+                value=world * n * steps / (ms * 1e-3), unit="particles/s", ms_per_step=ms / steps,
+                config=dict(workload="pf_full_iteration_2^20_particles_per_gpu",
+                            resampled_steps=st["resampled"], steps=steps,
+                            note="estimate copies xEst/PEst to the host every step (one stream sync per step)"))
+
+
 def cpu_pf(host=None, lm=None):
     from cpprobotics_b200 import synth
     from oracle import oracle as O
@@ -638,19 +674,22 @@ def run_ours(args):
     rank, world, local = dist_setup(args.gpus)
     eng = Engine(local)
     res = {}
+    cpu = (not args.no_cpu) and world == 1     # cpu_baseline: rank 0 at N = 1 only (the contract)
     with ClockSampler(local) as clk:
-        head = bench_ekf(eng, rank, world, args.steps, args.warmup, with_cpu=not args.no_cpu)
+        head = bench_ekf(eng, rank, world, args.steps, args.warmup, with_cpu=cpu)
         if args.workload in ("all", "pf"):
-            res["pf"] = bench_pf(eng, rank, world, args.steps, args.warmup, with_cpu=not args.no_cpu)
+            res["pf"] = bench_pf(eng, rank, world, args.steps, args.warmup, with_cpu=cpu)
+        if args.workload in ("all", "pf"):
+            res["pf_full_iteration"] = bench_pf_iteration(eng, rank, world, 10, 3)
         if args.workload in ("all", "ekf100"):
             res["ekf_100_steps"] = bench_ekf_multistep(eng, rank, world, 3, 2)
         if args.workload in ("all", "ekf16m"):
             res["ekf_16M_agents"] = bench_ekf_large(eng, rank, world, 5, 3)
         if args.workload in ("all", "lqr"):
-            res["lqr"] = bench_lqr(eng, rank, world, max(3, args.steps // 5), 3, with_cpu=not args.no_cpu)
+            res["lqr"] = bench_lqr(eng, rank, world, max(3, args.steps // 5), 3, with_cpu=cpu)
         if args.workload in ("all", "mpc"):
             res["mpc"] = bench_mpc(eng, rank, world, max(3, args.steps // 5), max(1, args.warmup // 3),
-                                   with_cpu=not args.no_cpu)
+                                   with_cpu=cpu)
     line = {
         "metric": "EKF updates/sec (4-state/2-obs predict+update, batched)",
         "value": head["value"], "unit": "updates/s", "n_gpus": world, "steps": args.steps,
