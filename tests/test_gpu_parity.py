@@ -599,3 +599,50 @@ def test_full_size_mpc_65536_bit_exact_vs_oracle(engine):
     for k in ("status", "iters", "u0", "cost", "sol"):
         assert np.array_equal(got[k], want[k]), k
     assert (got["status"] == 0).mean() > 0.999
+
+
+def test_full_size_resample_properties_2pow20(engine):
+    """Size-independent properties of resampling() at 2^20 particles (no oracle needed): the surviving source
+    indices are non-decreasing in j (both resampleid and the cumulative weights are monotone), every output
+    particle is a copy of an input particle, particle i survives within +-2 of n*w_i times (systematic
+    resampling with one jittered draw per slot), and the weights come back uniform."""
+    import torch
+    n = 1 << 20
+    rng = np.random.default_rng(11)
+    w = rng.gamma(0.3, 1.0, n).astype(np.float64)            # heavy-tailed weights
+    w[rng.integers(0, n, n // 4)] = 0.0                      # a quarter of the particles are dead
+    w = (w / w.sum()).astype(np.float32)
+    px = np.stack([np.arange(n, dtype=np.float32),           # field 0 = the particle's own index (exact < 2^24)
+                   rng.standard_normal(n).astype(np.float32),
+                   rng.standard_normal(n).astype(np.float32),
+                   rng.standard_normal(n).astype(np.float32)])
+    pxd, pwd = _dev(px, w)
+    did, neff = engine.pf_resample(pxd, pwd, seed=5, nth=float(n))
+    torch.cuda.synchronize()
+    assert did
+    out = pxd.cpu().numpy()
+    src = out[0].astype(np.int64)
+    assert (np.diff(src) >= 0).all()
+    assert np.array_equal(out[1:], px[1:, src])
+    counts = np.bincount(src, minlength=n)
+    assert np.abs(counts - n * w.astype(np.float64)).max() <= 2.0 + 1e-3 * n * w.max()
+    dead = w == 0
+    assert counts[:-1][dead[:-1]].sum() == 0           # dead particles never survive ...
+    assert not dead[-1] or counts[-1] <= 2             # ... except slot NP-1 catching the reference's cap (:139)
+    assert np.array_equal(pwd.cpu().numpy(), np.full(n, np.float32(1.0 / n)))
+
+
+def test_ekf_n_steps_is_the_composition_of_single_steps_bitwise(engine):
+    """n_steps = k in one launch (state kept in registers) must equal k launches of one step, bit for bit,
+    at the full 2^20-agent size."""
+    import torch
+    n, k = 1 << 20, 5
+    x, P, z, u = synth.ekf_inputs(n, n_steps=k)
+    a = _dev(x, P, z, u)
+    engine.ekf_estimation(*a, n_steps=k)
+    xb, Pb = _dev(x, P)
+    for s in range(k):
+        zs, us = _dev(z[2 * s:2 * s + 2], u[2 * s:2 * s + 2])
+        engine.ekf_estimation(xb, Pb, zs, us)
+    torch.cuda.synchronize()
+    assert torch.equal(a[0], xb) and torch.equal(a[1], Pb)
