@@ -39,7 +39,7 @@ sys.path.insert(0, ROOT)
 EKF_N = 1 << 20
 PF_N = int(os.environ.get("CRB_BENCH_PF_N", 1 << 20))     # diagnostics only: the contract workload is 2^20 x 8
 PF_LM = int(os.environ.get("CRB_BENCH_PF_LM", 8))
-MPC_N = 1 << 16
+MPC_N = int(os.environ.get("CRB_BENCH_MPC_N", 1 << 16))    # diagnostics only: the contract workload is 2^16
 MPC_T = 20
 MPC_ITER, MPC_DUTH, MPC_LS = 50, 1e-4, 4   # IPOPT's max_iter (:326); tight du so the NLP converges
 EKF_BYTES = 176       # read x4 P16 z2 u2, write x4 P16 (f32)            SURVEY §8 d-3
@@ -459,10 +459,10 @@ def mpc_flops(iters_sum, n, T):
     return iters_sum * (T - 1) * (470.0 + 1.2 * 150.0)
 
 
-def bench_mpc(eng, rank, world, steps, warmup, with_cpu):
+def bench_mpc(eng, rank, world, steps, warmup, with_cpu, n=None):
     import torch
     from cpprobotics_b200 import mpc_default_params, synth
-    n, T = MPC_N, MPC_T
+    n, T = (MPC_N if n is None else n), MPC_T
     dev = torch.device("cuda", torch.cuda.current_device())
     course = synth.mpc_course()
     st, pind = synth.mpc_states(n, i0=rank * n, course=course)
@@ -513,9 +513,9 @@ def bench_mpc(eng, rank, world, steps, warmup, with_cpu):
                                                         status=hstat, iters=hit), e_steps, 1, world)
     out = dict(metric="MPC solves/sec (T=20, bicycle model, box-constrained DDP to NLP convergence)",
                value=value, unit="solves/s", ms_per_step=ms / steps,
-               config=dict(workload="mpc_T20_65536_agents_per_gpu", max_iter=MPC_ITER, du_th=MPC_DUTH,
+               config=dict(workload=f"mpc_T20_{n}_agents_per_gpu", max_iter=MPC_ITER, du_th=MPC_DUTH,
                            max_ls=MPC_LS, stats_allgather="every step",
-                           l2="3 rotating input sets; solver workspace 131 MB > 126 MB L2"),
+                           l2=f"3 rotating input sets; solver workspace {n * 582 * 4 / 1e6:.0f} MB > 126 MB L2"),
                solver=dict(mean_iters=iters_sum / (world * n),
                            frac_converged=float(g[:, 4].sum()) / (world * n),
                            mean_cost=float(g[:, 0].sum()) / (world * n),
@@ -690,6 +690,11 @@ def run_ours(args):
         if args.workload in ("all", "mpc"):
             res["mpc"] = bench_mpc(eng, rank, world, max(3, args.steps // 5), max(1, args.warmup // 3),
                                    with_cpu=cpu)
+            # the same solver with the machine filled (BASELINE config 5's 2^20 agents on one GPU): the
+            # 2^16-agent contract size occupies 20 % of the resident-warp capacity
+            big = bench_mpc(eng, rank, world, 3, 1, with_cpu=False, n=1 << 20)
+            big["metric"] += ", 2^20 agents per GPU"
+            res["mpc_2^20_agents"] = big
     line = {
         "metric": "EKF updates/sec (4-state/2-obs predict+update, batched)",
         "value": head["value"], "unit": "updates/s", "n_gpus": world, "steps": args.steps,
