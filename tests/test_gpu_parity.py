@@ -646,3 +646,34 @@ def test_ekf_n_steps_is_the_composition_of_single_steps_bitwise(engine):
         engine.ekf_estimation(xb, Pb, zs, us)
     torch.cuda.synchronize()
     assert torch.equal(a[0], xb) and torch.equal(a[1], Pb)
+
+
+# ---- the CUDA path against outputs of the reference's own source text (tests/golden/ref_golden.npz) ------------
+def test_cuda_path_against_reference_text_outputs(engine):
+    """No oracle in between: EKF within the float tolerance (CUDA vs glibc sinf/cosf), DARE/LQR gains and the
+    reference-trajectory index work bit for bit, the plant update to 1e-5."""
+    import torch
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_golden.npz"))
+    xd, Pd, zd, ud = _dev(G["ekf_x"], G["ekf_P"], G["ekf_z"], G["ekf_u"])
+    engine.ekf_estimation(xd, Pd, zd, ud)
+    torch.cuda.synchronize()
+    assert field_err(xd.cpu().numpy(), G["ekf_x_out"]) <= 1e-5
+    assert field_err(Pd.cpu().numpy(), G["ekf_P_out"]) <= 1e-5
+    for nx, nu in ((4, 1), (5, 2)):
+        Ad, Bd, Qd, Rd = _dev(G[f"lqr{nx}_A"], G[f"lqr{nx}_B"], G[f"lqr{nx}_Q"], G[f"lqr{nx}_R"])
+        X = torch.empty((nx * nx, Ad.shape[1]), dtype=torch.float32, device="cuda")
+        K = engine.dlqr(Ad, Bd, Qd, Rd, nx, nu, X=X)
+        torch.cuda.synchronize()
+        assert np.array_equal(K.cpu().numpy(), G[f"lqr{nx}_K"]) and np.array_equal(X.cpu().numpy(), G[f"lqr{nx}_X"])
+    T = int(G["crt_T"])
+    course = synth.mpc_course()
+    std = _dev(G["crt_state"])[0]
+    tid = torch.from_numpy(G["crt_pind"].astype(np.int32)).cuda()
+    xr = torch.empty((4 * T, std.shape[1]), dtype=torch.float32, device="cuda")
+    engine.calc_ref_trajectory(std, *_dev(*course), 1.0, tid, xr, T)
+    torch.cuda.synchronize()
+    assert np.array_equal(tid.cpu().numpy(), G["crt_tind"]) and np.array_equal(xr.cpu().numpy(), G["crt_xref"])
+    sd, u0d = _dev(G["upd_state"], np.stack([G["upd_a"], G["upd_delta"]]))
+    engine.mpc_plant_update(sd, u0d)
+    torch.cuda.synchronize()
+    assert np.abs(sd.cpu().numpy() - G["upd_out"]).max() <= 1e-5 * np.abs(G["upd_out"]).max()
