@@ -22,6 +22,34 @@ f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
 i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
 
 
+FAST_LIB_PATH = os.path.join(_HERE, "lib", "liboracle_fast.so")
+_libs = {}
+
+
+def use_library(which: str = "faithful") -> bool:
+    """Selects the build the wrappers below call: "faithful" = liboracle.so (-O2 -ffp-contract=off, the
+    parity oracle), "fast" = liboracle_fast.so (same sources, -O3 -march=x86-64-v3 -ffp-contract=fast:
+    BASELINE.md's B2 "what the host can do" timing arm; NOT a parity reference).  Returns False (and
+    keeps the faithful build) when the fast build is missing or the CPU lacks AVX2/FMA."""
+    global _lib, LIB_PATH
+    want = os.path.join(_HERE, "lib", "liboracle.so")
+    ok = True
+    if which == "fast":
+        flags = ""
+        try:
+            flags = open("/proc/cpuinfo").read()
+        except OSError:
+            pass
+        if os.path.exists(FAST_LIB_PATH) and " avx2" in flags and " fma" in flags:
+            want = FAST_LIB_PATH
+        else:
+            ok = False
+    _libs[LIB_PATH] = _lib
+    LIB_PATH = want
+    _lib = _libs.get(want)
+    return ok
+
+
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
