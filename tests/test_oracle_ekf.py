@@ -3,6 +3,7 @@ float64 numpy statement of src/extended_kalman_filter.cpp:22-78, and the committ
 import os
 
 import numpy as np
+import pytest
 
 from cpprobotics_b200 import synth
 from oracle import oracle as O
@@ -124,3 +125,20 @@ def test_golden_vectors():
     # and against the float64 numpy statement stored beside it
     assert (np.abs(xo - g["x_f64"]).max(axis=0) / np.abs(g["x_f64"]).max(axis=0)).max() <= 1e-5
     assert (np.abs(Po - g["P_f64"]).max(axis=0) / np.abs(g["P_f64"]).max(axis=0)).max() <= 1e-5
+
+
+def test_best_effort_build_is_a_timing_arm_that_stays_close():
+    """oracle/lib/liboracle_fast.so (-O3 -march=x86-64-v3 -ffp-contract=fast, bench.py's best_effort_value) is the
+    same source: results within the float tolerance of the faithful build, and the switch is reversible."""
+    x, P, z, u = synth.ekf_inputs(2000, seed=5)
+    xa, Pa = O.ekf_step_batched(x, P, z, u, nthreads=1)
+    try:
+        if not O.use_library("fast"):
+            pytest.skip("fast build or AVX2/FMA not available")
+        xb, Pb = O.ekf_step_batched(x, P, z, u, nthreads=1)
+    finally:
+        O.use_library("faithful")
+    xc, Pc = O.ekf_step_batched(x, P, z, u, nthreads=1)
+    assert np.array_equal(xa, xc) and np.array_equal(Pa, Pc)
+    err = lambda g, w: (np.abs(g - w).max(axis=0) / np.abs(w).max(axis=0)).max()  # noqa: E731
+    assert err(xb, xa) <= 1e-5 and err(Pb, Pa) <= 1e-5
