@@ -25,9 +25,15 @@
  *   - All batched arrays are SoA, "field-major": element (field f, agent i) lives at ptr[f*n + i].
  *     Matrices are flattened column-major like Eigen fixed-size matrices: P(r,c) is field r + 4*c.
  *   - Entry points without a suffix take DEVICE pointers and enqueue asynchronously on the context's
- *     stream; `_host` variants take HOST pointers (pinned memory recommended, see crb_host_alloc),
- *     stage through internal device buffers in chunks with copy/compute overlap, and return after
- *     the results are in the caller's buffers.
+ *     stream; `_host` variants take HOST pointers and return after the results are in the caller's
+ *     buffers.  When every array of the call is pinned and mapped into the device's address space
+ *     (crb_host_alloc, cudaHostAlloc / cudaMallocHost, cudaHostRegister) the EKF and PF kernels run
+ *     directly on that memory over PCIe (no staging copy) and the MPC solver stores its results
+ *     straight into it; any other host memory is staged through internal device buffers in chunks with
+ *     copy/compute overlap.  Both routes give the same bits.  CRB_HOST_ZEROCOPY=0 forces staging.
+ *   - Back-to-back EKF / PF step launches on one stream use programmatic dependent launch (the next
+ *     launch's prologue overlaps the previous launch's tail; data dependencies are still honoured).
+ *     CRB_PDL=0 disables it.
  *   - Return value: CRB_OK (0) or a negative crb_status.  crb_last_error_string() describes the last
  *     failure on the calling thread.  The reference reports no errors at all (IPOPT status is dropped,
  *     src/model_predictive_control.cpp:338-339); the per-agent MPC status word is additional.
@@ -74,7 +80,7 @@ void* crb_get_stream(crb_ctx* ctx);
 int crb_sync(crb_ctx* ctx);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 int64_t crb_launch_count(crb_ctx* ctx);
-/* Pinned host memory helpers for the _host entry points. */
+/* Pinned, device-mapped host memory for the _host entry points (enables their zero-copy route). */
 int crb_host_alloc(void** out, size_t bytes);
 int crb_host_free(void* p);
 /* Device memory helpers (for callers that do not want to link the CUDA runtime themselves). */
