@@ -7,7 +7,7 @@ from cpprobotics_b200 import synth
 from oracle import oracle as O
 
 SEEDS = st.integers(min_value=1, max_value=2**31 - 1)
-FAST = settings(max_examples=8, deadline=None)
+FAST = settings(max_examples=int(__import__("os").environ.get("CRB_HYP_EXAMPLES", 8)), deadline=None, derandomize=True, database=None)
 
 
 @FAST
