@@ -7,6 +7,8 @@
 //   mpc_solve(x0, traj_ref)                       src/model_predictive_control.cpp:255-346
 //   update(state, a, delta)                       src/model_predictive_control.cpp:69-81
 //   calc_ref_trajectory(...)                      src/model_predictive_control.cpp:130-170
+//   resampling(px, pw, gen, uni_d)                src/particle_filter.cpp:120-148
+//   solve_DARE / dlqr (4x4 and 5x5)               src/lqr_steer_control.cpp:75-96, lqr_speed_steer_control.cpp:85-106
 //
 // Eigen is not a dependency: crb::Mat<R,C> is a POD with the memory layout of
 // Eigen::Matrix<float,R,C> (column-major, contiguous, no padding), enough of its interface for the
@@ -233,6 +235,91 @@ inline void pf_localization(crb::Mat<4, NP>& px, crb::Mat<NP, 1>& pw, crb::Vecto
   for (int ip = 0; ip < NP; ++ip)
     for (int k = 0; k < 4; ++k) px(k, ip) = sx[k * NP + ip];
   crb_device_free(ctx, dpx); crb_device_free(ctx, dpw); crb_device_free(ctx, dn);
+}
+
+// src/particle_filter.cpp:120-148.  gen and uni_d BY VALUE like the reference (:122-123: the caller's
+// generator is not advanced, so every call sees the same draws - the reference's quirk).  The NP draws
+// are made here in the reference's order (one per particle, :133) and handed to the engine as its
+// explicit uniforms; NTh = NP/2 (:22).  Deviations (documented in crb.h): the cumulative weights are
+// accumulated in double, the draw is narrowed to float before use.
+template <int NP>
+inline void resampling(crb::Mat<4, NP>& px, crb::Mat<NP, 1>& pw, std::mt19937 gen,
+                       std::uniform_real_distribution<> uni_d) {
+  crb_ctx* ctx = crb::Session::get();
+  std::vector<float> sx(4 * NP), un(NP);
+  for (int ip = 0; ip < NP; ++ip) {
+    for (int k = 0; k < 4; ++k) sx[k * NP + ip] = px(k, ip);
+    un[ip] = (float)uni_d(gen);
+  }
+  void *dpx = nullptr, *dpw = nullptr, *dtmp = nullptr, *du = nullptr;
+  crb::check(crb_device_alloc(ctx, &dpx, sx.size() * sizeof(float)), "crb_device_alloc");
+  crb::check(crb_device_alloc(ctx, &dtmp, sx.size() * sizeof(float)), "crb_device_alloc");
+  crb::check(crb_device_alloc(ctx, &dpw, NP * sizeof(float)), "crb_device_alloc");
+  crb::check(crb_device_alloc(ctx, &du, NP * sizeof(float)), "crb_device_alloc");
+  crb::check(crb_memcpy_h2d(ctx, dpx, sx.data(), sx.size() * sizeof(float)), "h2d");
+  crb::check(crb_memcpy_h2d(ctx, dpw, pw.data(), NP * sizeof(float)), "h2d");
+  crb::check(crb_memcpy_h2d(ctx, du, un.data(), NP * sizeof(float)), "h2d");
+  int did = 0;
+  crb::check(crb_pf_resample(ctx, NP, (float*)dpx, (float*)dpw, (float*)dtmp, (const float*)du, 0,
+                             (float)(NP / 2.0), &did, nullptr),
+             "crb_pf_resample");
+  if (did) {
+    crb::check(crb_memcpy_d2h(ctx, sx.data(), dpx, sx.size() * sizeof(float)), "d2h");
+    crb::check(crb_memcpy_d2h(ctx, pw.data(), dpw, NP * sizeof(float)), "d2h");
+    for (int ip = 0; ip < NP; ++ip)
+      for (int k = 0; k < 4; ++k) px(k, ip) = sx[k * NP + ip];
+  }
+  crb_device_free(ctx, dpx); crb_device_free(ctx, dtmp); crb_device_free(ctx, dpw); crb_device_free(ctx, du);
+}
+
+// solve_DARE + dlqr: src/lqr_steer_control.cpp:75-96 (nx = 4, scalar R) and
+// src/lqr_speed_steer_control.cpp:85-106 (nx = 5, 2x2 R).  One problem per call through the batched entry.
+namespace crb {
+using Matrix5f = Mat<5, 5>;
+using Matrix52f = Mat<5, 2>;
+using Matrix25f = Mat<2, 5>;
+using RowVector4f = Mat<1, 4>;
+
+template <int NX, int NU>
+inline void dlqr_impl(const float* A, const float* B, const float* Q, const float* R, float* K, float* X) {
+  crb_ctx* ctx = Session::get();
+  const size_t na = NX * NX, nb = NX * NU, nr = NU * NU, nk = NU * NX;
+  void* d = nullptr;
+  check(crb_device_alloc(ctx, &d, (2 * na + nb + nr + nk + na) * sizeof(float)), "crb_device_alloc");
+  float* dA = (float*)d;
+  float *dB = dA + na, *dQ = dB + nb, *dR = dQ + na, *dK = dR + nr, *dX = dK + nk;
+  check(crb_memcpy_h2d(ctx, dA, A, na * sizeof(float)), "h2d");
+  check(crb_memcpy_h2d(ctx, dB, B, nb * sizeof(float)), "h2d");
+  check(crb_memcpy_h2d(ctx, dQ, Q, na * sizeof(float)), "h2d");
+  check(crb_memcpy_h2d(ctx, dR, R, nr * sizeof(float)), "h2d");
+  check(crb_lqr_dlqr_batched(ctx, 1, NX, NU, dA, dB, dQ, dR, /*maxiter :77*/ 150, /*eps :78*/ 0.01f, dK, dX,
+                             nullptr),
+        "crb_lqr_dlqr_batched");
+  if (K) check(crb_memcpy_d2h(ctx, K, dK, nk * sizeof(float)), "d2h");
+  if (X) check(crb_memcpy_d2h(ctx, X, dX, na * sizeof(float)), "d2h");
+  crb_device_free(ctx, d);
+}
+}  // namespace crb
+
+inline crb::Matrix4f solve_DARE(crb::Matrix4f A, crb::Vector4f B, crb::Matrix4f Q, float R) {
+  crb::Matrix4f X;
+  crb::dlqr_impl<4, 1>(A.data(), B.data(), Q.data(), &R, nullptr, X.data());
+  return X;
+}
+inline crb::RowVector4f dlqr(crb::Matrix4f A, crb::Vector4f B, crb::Matrix4f Q, float R) {
+  crb::RowVector4f K;
+  crb::dlqr_impl<4, 1>(A.data(), B.data(), Q.data(), &R, K.data(), nullptr);
+  return K;
+}
+inline crb::Matrix5f solve_DARE(crb::Matrix5f A, crb::Matrix52f B, crb::Matrix5f Q, crb::Matrix2f R) {
+  crb::Matrix5f X;
+  crb::dlqr_impl<5, 2>(A.data(), B.data(), Q.data(), R.data(), nullptr, X.data());
+  return X;
+}
+inline crb::Matrix25f dlqr(crb::Matrix5f A, crb::Matrix52f B, crb::Matrix5f Q, crb::Matrix2f R) {
+  crb::Matrix25f K;
+  crb::dlqr_impl<5, 2>(A.data(), B.data(), Q.data(), R.data(), K.data(), nullptr);
+  return K;
 }
 
 #endif  // CRB_REFERENCE_API_HPP_

@@ -36,6 +36,15 @@ def make_inputs():
     return np.concatenate([np.asarray(b, np.float32).reshape(-1) for b in buf]), zu, course, st, px, pw, lm
 
 
+def test_every_reference_signature_compiles_and_links(tmp_path):
+    """ekf_estimation, pf_localization, resampling, mpc_solve, update, calc_ref_trajectory, solve_DARE and dlqr
+    (both LQR demos) with the argument types a CppRobotics main() passes: -std=c++11 -Wall -Werror."""
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call(["g++", "-std=c++11", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "ref_api_all_signatures.cpp"), "-L", libdir, "-lcrb",
+                           f"-Wl,-rpath,{libdir}", "-o", str(tmp_path / "ref_sig")])
+
+
 def test_compiles_links_and_fails_loudly_without_gpu(tmp_path):
     import torch
     exe = build(tmp_path)
