@@ -97,3 +97,46 @@ def test_reference_style_main_matches_oracle(tmp_path):
     assert np.abs(pwg - pwn).max() <= 2e-3 * np.abs(pwn).max()       # weight conditioning, see DESIGN.md 3.2
     assert np.abs(xeg - xeo).max() <= 1e-3 and np.abs(Peg - Peo.T.reshape(-1)).max() <= 1e-3
     assert p == out.size
+
+
+# ---- resampling / solve_DARE / dlqr shims: marshalling checked on the CPU through a mock of the C ABI ------------
+def _shim_inputs():
+    px, pw, noise = synth.pf_inputs(NP, seed=21)
+    lm = synth.pf_landmarks(4, seed=21)
+    px, pw = O.pf_predict_weight_batched(px, pw, noise, lm)          # peaked weights -> Neff < NP/2 -> resample
+    pw = (pw / np.float32(pw.sum())).astype(np.float32)
+    A4, B4, Q4, R4 = synth.lqr_inputs(1, 4, seed=5)
+    A5, B5, Q5, R5 = synth.lqr_inputs(1, 5, seed=5)
+    blob = np.concatenate([np.float32([4321]), px.T.reshape(-1), pw, A4[:, 0], B4[:, 0], Q4.reshape(-1),
+                           np.float32([R4.reshape(-1)[0]]), A5[:, 0], B5[:, 0], Q5.reshape(-1),
+                           R5.reshape(-1)]).astype(np.float32)
+    return blob, px, pw, (A4, B4, Q4, R4), (A5, B5, Q5, R5)
+
+
+def _check_shim_outputs(out, px, pw, l4, l5):
+    gpx, gpw, draws = out[:400].reshape(NP, 4).T, out[400:500], out[500:600]
+    assert (draws >= 1.0).all() and (draws <= 2.0).all()
+    pxo, pwo, did, _ = O.pf_resample(px, pw, draws.astype(np.float64))
+    assert did and np.array_equal(gpx, pxo) and np.array_equal(gpw, pwo)
+    p = 600
+    for (A, B, Q, R), nx, nu in ((l4, 4, 1), (l5, 5, 2)):
+        r = O.dlqr_batched(A, B, Q, R, nx, nu)
+        X, K = out[p:p + nx * nx], out[p + nx * nx:p + nx * nx + nu * nx]
+        p += nx * nx + nu * nx
+        assert np.array_equal(X, r["X"][:, 0]) and np.array_equal(K, r["K"][:, 0])
+    assert p == out.size
+
+
+def test_resampling_and_dlqr_shims_marshal_correctly_through_a_cpu_mock(tmp_path):
+    """tests/cpp/mock_crb.c implements the few C-ABI calls these shims make with the oracle, so their AoS<->SoA
+    and column-major marshalling and the by-value RNG semantics are executed and checked without a GPU."""
+    odir = os.path.join(ROOT, "oracle", "lib")
+    obj, exe = str(tmp_path / "mock_crb.o"), str(tmp_path / "shim_check")
+    subprocess.check_call(["gcc", "-O1", "-Wall", "-c", os.path.join(ROOT, "tests", "cpp", "mock_crb.c"), "-o", obj])
+    subprocess.check_call(["g++", "-std=c++11", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "ref_api_shim_check.cpp"), obj, "-L", odir, "-loracle",
+                           f"-Wl,-rpath,{odir}", "-o", exe])
+    blob, px, pw, l4, l5 = _shim_inputs()
+    blob.tofile(tmp_path / "in.bin")
+    subprocess.check_call([exe, str(tmp_path / "in.bin"), str(tmp_path / "out.bin")])
+    _check_shim_outputs(np.fromfile(tmp_path / "out.bin", np.float32), px, pw, l4, l5)
