@@ -28,6 +28,9 @@ struct crb_ctx {
   void* mpc_ws;
   size_t mpc_ws_cap;
   void* host_scratch;  // small pinned buffer for reduction results
+  // per-device function attributes already set for this context's device (a second context on another
+  // device in the same process must set them again, so these are not process-global latches)
+  int mpc_tasks_attr_set;
 };
 
 void crb_set_error(const char* fmt, ...);

@@ -27,175 +27,15 @@
 
 #include "crb_common.cuh"
 
-struct MpcP {
-  float dt, inv_dt, inv_wb, max_steer, max_accel, max_speed, min_speed;
-  float w_a, w_delta, w_da, w_ddelta;
-  float wq[4];
-  int max_iter;
-  float du_th;
-  int max_ls;
-  float j_tol;
-};
+#include "crb_mpc_core.cuh"
+#include "crb_mpc_tasks.cuh"
 
-#define REG_EPS 1.0e-3f
-#define NGAIN 14  // k[2], Kx[2][4], Kw[2][2]
-// Solver workspace layout: CTA-interleaved.  A CTA of MPC_BLOCK threads owns a contiguous slab
-// [item][MPC_BLOCK]; thread t of the CTA reads item k at slab[k*MPC_BLOCK + t].  Accesses stay coalesced
-// (MPC_BLOCK consecutive floats per item) and every per-thread offset is a COMPILE-TIME constant times the
-// item index, so loads/stores use immediate offsets instead of two 64-bit adds each (address arithmetic
-// was the largest instruction class of the first version of this kernel).
+// Thread-per-problem kernel (first generation; CRB_MPC_VARIANT=0): solver workspace in global memory,
+// CTA-interleaved.  A CTA of MPC_BLOCK threads owns a contiguous slab [item][MPC_BLOCK]; thread t of the
+// CTA reads item k at slab[k*MPC_BLOCK + t].  Accesses stay coalesced (MPC_BLOCK consecutive floats per
+// item) and every per-thread offset is a COMPILE-TIME constant times the item index.
 #define MPC_BLOCK 128
 #define LS MPC_BLOCK
-
-// sin/cos: Cody-Waite reduction by pi/2 + minimax polynomials (same operations as the oracle's
-// crb_oracle_sincosf; libm / CUDA sinf are NOT used so that CPU and GPU agree to the bit).
-__device__ __forceinline__ void crb_sincosf(float x, float& sn, float& cs) {
-  if (!(fabsf(x) <= 1.0e5f)) {
-    sn = x - x;
-    cs = x - x;
-    if (fabsf(x) > 1.0e5f && x - x == 0.0f) {
-      sn = 0.0f;
-      cs = 1.0f;
-    }
-    return;
-  }
-  const float j = rintf(x * 0.63661977236758134308f);
-  float r = fmaf(-j, 1.5707962512969970703125f, x);
-  r = fmaf(-j, 7.5497894158615963533521e-08f, r);
-  r = fmaf(-j, 5.3903029534742383e-15f, r);
-  const int q = (int)j & 3;
-  const float z = r * r;
-  float ps = fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f);
-  ps = fmaf(ps, z, -1.6666654611e-1f);
-  ps = ps * z;
-  ps = fmaf(ps, r, r);
-  float pc = fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f);
-  pc = fmaf(pc, z, 4.166664568298827e-2f);
-  pc = pc * z;
-  pc = fmaf(pc, z, fmaf(-0.5f, z, 1.0f));
-  float s_ = (q & 1) ? pc : ps;
-  float c_ = (q & 1) ? ps : pc;
-  if (q & 2) s_ = -s_;
-  if ((q + 1) & 2) c_ = -c_;
-  sn = s_;
-  cs = c_;
-}
-
-__device__ __forceinline__ void a_bounds(float v, const MpcP& p, float& lo, float& hi, bool& lo_sp,
-                                         bool& hi_sp) {
-  const float lo_v = (p.min_speed - v) * p.inv_dt;
-  const float hi_v = (p.max_speed - v) * p.inv_dt;
-  const float am = p.max_accel;
-  float l = lo_v < am ? lo_v : am;
-  l = l > -am ? l : -am;
-  float h = hi_v > -am ? hi_v : -am;
-  h = h < am ? h : am;
-  lo = l;
-  hi = h;
-  lo_sp = lo_v > -am;
-  hi_sp = hi_v < am;
-}
-
-__device__ __forceinline__ float clampf(float u, float lo, float hi) {
-  return u < lo ? lo : (u > hi ? hi : u);
-}
-
-// x_{t+1} = f(x_t, u_t), src/model_predictive_control.cpp:242-245
-__device__ __forceinline__ void dyn_step(const float (&x)[4], float delta, float a, const MpcP& p,
-                                         float (&xn)[4]) {
-  float s, c, sd, cd;
-  crb_sincosf(x[2], s, c);
-  crb_sincosf(delta, sd, cd);
-  const float kap = (sd / cd) * p.inv_wb;
-  const float vdt = x[3] * p.dt;
-  xn[0] = fmaf(vdt, c, x[0]);
-  xn[1] = fmaf(vdt, s, x[1]);
-  xn[2] = fmaf(vdt, kap, x[2]);
-  xn[3] = fmaf(a, p.dt, x[3]);
-}
-
-struct QpResult {
-  float k0, k1;
-  bool cl0, cl1;
-  float H00, H11;  // regularised diagonal used for the gains (H01 is never changed)
-  float idet, ih00, ih11;
-};
-
-// Projected-Newton step of the 2-D box QP (see box_qp2 in the oracle: same operations, same order).
-__device__ __forceinline__ void box_qp2(float Q00, float Q01, float Q11, float g0, float g1,
-                                        float lo0, float lo1, float hi0, float hi1, QpResult& r) {
-  const bool sa0lo = lo0 >= 0.0f && g0 > 0.0f, sa0hi = !sa0lo && hi0 <= 0.0f && g0 < 0.0f;
-  const bool sa1lo = lo1 >= 0.0f && g1 > 0.0f, sa1hi = !sa1lo && hi1 <= 0.0f && g1 < 0.0f;
-  const bool sa0 = sa0lo || sa0hi, sa1 = sa1lo || sa1hi;
-  r.H00 = Q00; r.H11 = Q11; r.idet = 0.0f; r.ih00 = 0.0f; r.ih11 = 0.0f;
-  r.k0 = 0.0f; r.k1 = 0.0f;
-  if (sa0) r.k0 = sa0lo ? lo0 : hi0;
-  if (sa1) r.k1 = sa1lo ? lo1 : hi1;
-  if (sa0 && sa1) { r.cl0 = true; r.cl1 = true; return; }
-  if (sa0) {
-    r.H11 = fabsf(Q11) > REG_EPS ? fabsf(Q11) : REG_EPS;
-    r.ih11 = 1.0f / r.H11;
-    float uj = -(fmaf(Q01, r.k0, g1) * r.ih11);
-    bool cj = false;
-    if (uj <= lo1) { uj = lo1; cj = true; }
-    else if (uj >= hi1) { uj = hi1; cj = true; }
-    r.k1 = uj; r.cl0 = true; r.cl1 = cj;
-    return;
-  }
-  if (sa1) {
-    r.H00 = fabsf(Q00) > REG_EPS ? fabsf(Q00) : REG_EPS;
-    r.ih00 = 1.0f / r.H00;
-    float uj = -(fmaf(Q01, r.k1, g0) * r.ih00);
-    bool cj = false;
-    if (uj <= lo0) { uj = lo0; cj = true; }
-    else if (uj >= hi0) { uj = hi0; cj = true; }
-    r.k0 = uj; r.cl1 = true; r.cl0 = cj;
-    return;
-  }
-  const float mh = 0.5f * (Q00 + Q11), dh = 0.5f * (Q00 - Q11);
-  const float lam = mh - sqrtf(fmaf(dh, dh, Q01 * Q01));
-  const float shift = lam < REG_EPS ? (-lam > REG_EPS ? -lam : REG_EPS) - lam : 0.0f;
-  const float H00 = Q00 + shift, H11 = Q11 + shift, H01 = Q01;
-  const float det = fmaf(H00, H11, -(H01 * H01));
-  const float idet = 1.0f / det, ih00 = 1.0f / H00, ih11 = 1.0f / H11;
-  r.H00 = H00; r.H11 = H11; r.idet = idet; r.ih00 = ih00; r.ih11 = ih11;
-  const float n0 = fmaf(H01, g1, -(H11 * g0));
-  const float n1 = fmaf(H01, g0, -(H00 * g1));
-  const float u0 = n0 * idet, u1 = n1 * idet;
-  if (u0 >= lo0 && u0 <= hi0 && u1 >= lo1 && u1 <= hi1) {
-    r.k0 = u0; r.k1 = u1; r.cl0 = false; r.cl1 = false;
-    return;
-  }
-  float best = INFINITY;
-  r.k0 = lo0 > 0.0f ? lo0 : (hi0 < 0.0f ? hi0 : 0.0f);
-  r.k1 = lo1 > 0.0f ? lo1 : (hi1 < 0.0f ? hi1 : 0.0f);
-  r.cl0 = true; r.cl1 = true;
-  // edges with u0 fixed (i = 0, j = 1), then u1 fixed (i = 1, j = 0); lo side before hi side
-#pragma unroll
-  for (int side = 0; side < 2; ++side) {
-    const float b = side ? hi0 : lo0;
-    float uj = -(fmaf(H01, b, g1) * ih11);
-    bool cj = false;
-    if (uj <= lo1) { uj = lo1; cj = true; }
-    else if (uj >= hi1) { uj = hi1; cj = true; }
-    const float ti = fmaf(0.5f * H00, b, g0);
-    const float tj = fmaf(0.5f * H11, uj, g1);
-    const float val = fmaf(ti, b, fmaf(tj, uj, (H01 * b) * uj));
-    if (val < best) { best = val; r.k0 = b; r.k1 = uj; r.cl0 = true; r.cl1 = cj; }
-  }
-#pragma unroll
-  for (int side = 0; side < 2; ++side) {
-    const float b = side ? hi1 : lo1;
-    float uj = -(fmaf(H01, b, g0) * ih00);
-    bool cj = false;
-    if (uj <= lo0) { uj = lo0; cj = true; }
-    else if (uj >= hi0) { uj = hi0; cj = true; }
-    const float ti = fmaf(0.5f * H11, b, g1);
-    const float tj = fmaf(0.5f * H00, uj, g0);
-    const float val = fmaf(ti, b, fmaf(tj, uj, (H01 * b) * uj));
-    if (val < best) { best = val; r.k1 = b; r.k0 = uj; r.cl1 = true; r.cl0 = cj; }
-  }
-}
 
 // ---- backward sweep -------------------------------------------------------------------------------
 // X [4T][n], U [2(T-1)][n] (field 2t+c, c = 0 delta, 1 a), xref [4T][n] (course frame; ox, oy are
@@ -745,9 +585,23 @@ static void mpc_fill(MpcP* p, const crb_mpc_params* prm) {
   p->j_tol = prm->j_tol;
 }
 
-// workspace floats for `count` problems (whole CTAs)
-static size_t mpc_scratch_floats(int T, int64_t count) {
-  const size_t ctas = (size_t)((count + MPC_BLOCK - 1) / MPC_BLOCK);
+// Which solver kernel: 1 (default) = resident-slot task kernel (crb_mpc_tasks.cu), 0 = the first-generation
+// thread-per-problem kernel below (CRB_MPC_VARIANT=0; kept for A/B and as the specification of the mapping
+// the task kernel replaced).  Both produce the same bits.
+static int mpc_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CRB_MPC_VARIANT");
+    v = e ? atoi(e) : 1;
+    if (v != 0) v = 1;
+  }
+  return v;
+}
+
+// solver scratch in floats for `count` problems
+static size_t mpc_scratch_floats(crb_ctx* ctx, int T, int64_t count) {
+  if (mpc_variant() == 1) return (crb_mpc_tasks_scratch_bytes(ctx->sm_count, T, count) + 3) / 4;
+  const size_t ctas = (size_t)((count + MPC_BLOCK - 1) / MPC_BLOCK);  // whole CTAs
   return ctas * (size_t)mpc_ws_items(T) * MPC_BLOCK;
 }
 
@@ -758,6 +612,9 @@ static int mpc_launch(crb_ctx* ctx, cudaStream_t st, int64_t count, int64_t ld, 
                       int32_t* iters, const crb_mpc_params* prm) {
   MpcP p;
   mpc_fill(&p, prm);
+  if (mpc_variant() == 1)
+    return crb_mpc_tasks_launch(ctx, st, count, ld, T, x0, xref, u_init, scratch, ld_out, sol, u0, cost,
+                                status, iters, p);
   // Experiment kept for A/B (CRB_MPC_L2=1): an L2 persisting access-policy window over the solver
   // workspace.  Measured on B200: 36.1 M solves/s with it vs 60.0 M without (the set-aside shrinks the
   // normal L2 and the 152 MB workspace thrashes it), so it is OFF by default.
@@ -796,7 +653,7 @@ static int mpc_launch(crb_ctx* ctx, cudaStream_t st, int64_t count, int64_t ld, 
   cudaLaunchAttribute attr[1];
   int nattr = 0;
   if (l2_mode) {
-    size_t bytes = mpc_scratch_floats(T, count) * sizeof(float);
+    size_t bytes = mpc_scratch_floats(ctx, T, count) * sizeof(float);
     if (bytes > l2_max_window) bytes = l2_max_window;
     attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
     attr[0].val.accessPolicyWindow.base_ptr = scratch;
@@ -855,7 +712,7 @@ extern "C" int crb_mpc_solve_batched(crb_ctx* ctx, int64_t n, int T, const float
   int rc = mpc_check(ctx, n, T, x0, xref, prm);
   if (rc) return rc;
   if (n == 0) return CRB_OK;
-  rc = crb_ctx_mpc_ws_reserve(ctx, mpc_scratch_floats(T, n) * sizeof(float));
+  rc = crb_ctx_mpc_ws_reserve(ctx, mpc_scratch_floats(ctx, T, n) * sizeof(float));
   if (rc) return rc;
   return mpc_launch(ctx, ctx->stream, n, n, T, x0, xref, u_init, (float*)ctx->mpc_ws, n, sol,
                     u0, cost, status, iters, prm);
@@ -884,7 +741,7 @@ extern "C" int crb_mpc_solve_batched_host(crb_ctx* ctx, int64_t n, int T, const 
   const size_t nf = (size_t)4 + 4 * T + 2 * N + nsol + 5;
   const size_t pitch = (size_t)chunk_cap * sizeof(float);
   for (int s = 0; s < CRB_N_PIPE; ++s) {
-    rc = crb_ctx_pipe_reserve(ctx, s, nf * pitch + mpc_scratch_floats(T, chunk_cap) * sizeof(float));
+    rc = crb_ctx_pipe_reserve(ctx, s, nf * pitch + mpc_scratch_floats(ctx, T, chunk_cap) * sizeof(float));
     if (rc) return rc;
   }
   const size_t hp = (size_t)n * sizeof(float);
