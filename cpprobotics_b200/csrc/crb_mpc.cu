@@ -799,12 +799,31 @@ extern "C" int crb_mpc_solve_batched_host(crb_ctx* ctx, int64_t n, int T, const 
 // ---- update(): src/model_predictive_control.cpp:69-81 ------------------------------------------------
 // MAX_STEER, DT, WB, MAX_SPEED, MIN_SPEED are double macros in the reference, so the float operands
 // promote to double and the result narrows on assignment; cos/sin/tan are the float overloads.
+// The constants come from crb_mpc_params (floats).  A parameter that equals the reference's macro rounded to
+// float is taken as the macro's own double value (so the defaults reproduce the reference bit for bit);
+// any other value is promoted from float.  The solver, the plant step and the xref lookup therefore always
+// use the same model.
+struct MpcPlantC {
+  double max_steer, dt, wb, max_speed, min_speed;
+};
+static double mpc_promote(float v, double ref) { return v == (float)ref ? ref : (double)v; }
+static MpcPlantC mpc_plant_constants(const crb_mpc_params* prm) {
+  MpcPlantC c;
+  c.max_steer = mpc_promote(prm->max_steer, 45.0 / 180 * 3.14159265358979323846);
+  c.dt = mpc_promote(prm->dt, 0.2);
+  c.wb = mpc_promote(prm->wb, 2.5);
+  c.max_speed = mpc_promote(prm->max_speed, 55.0 / 3.6);
+  c.min_speed = mpc_promote(prm->min_speed, -20.0 / 3.6);
+  return c;
+}
+
 __global__ void __launch_bounds__(256)
-crb_mpc_plant_update_kernel(int64_t n, float* __restrict__ state, const float* __restrict__ u0) {
+crb_mpc_plant_update_kernel(int64_t n, float* __restrict__ state, const float* __restrict__ u0,
+                            const MpcPlantC k) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const double MAX_STEER = 45.0 / 180 * 3.14159265358979323846, DT = 0.2, WB = 2.5;
-  const double MAX_SPEED = 55.0 / 3.6, MIN_SPEED = -20.0 / 3.6;
+  const double MAX_STEER = k.max_steer, DT = k.dt, WB = k.wb;
+  const double MAX_SPEED = k.max_speed, MIN_SPEED = k.min_speed;
   const float a = u0[i];
   float delta = u0[n + i];
   if ((double)delta >= MAX_STEER) delta = (float)MAX_STEER;
@@ -822,11 +841,13 @@ crb_mpc_plant_update_kernel(int64_t n, float* __restrict__ state, const float* _
 extern "C" int crb_mpc_plant_update_batched(crb_ctx* ctx, int64_t n, float* state, const float* u0,
                                             const crb_mpc_params* prm) {
   CRB_REQUIRE(ctx != nullptr, "ctx is NULL");
+  CRB_REQUIRE(prm != nullptr, "prm is NULL");
   CRB_REQUIRE(n >= 0, "n < 0");
-  (void)prm;  // update() uses the reference's compile-time macros, mirrored in the kernel
+  CRB_REQUIRE(prm->dt > 0.0f && prm->wb > 0.0f, "dt and wb must be positive");
   if (n == 0) return CRB_OK;
   CRB_REQUIRE(state && u0, "NULL array");
-  crb_mpc_plant_update_kernel<<<crb_grid_for(n, 256), 256, 0, ctx->stream>>>(n, state, u0);
+  crb_mpc_plant_update_kernel<<<crb_grid_for(n, 256), 256, 0, ctx->stream>>>(n, state, u0,
+                                                                             mpc_plant_constants(prm));
   CRB_CUDA(cudaGetLastError());
   ctx->launches++;
   return CRB_OK;
@@ -837,7 +858,8 @@ __global__ void __launch_bounds__(256)
 crb_mpc_ref_traj_kernel(int64_t n, int T, const float* __restrict__ state,
                         const float* __restrict__ cx, const float* __restrict__ cy,
                         const float* __restrict__ cyaw, const float* __restrict__ sp, int ncourse,
-                        float dl, int32_t* __restrict__ target_ind, float* __restrict__ xref) {
+                        float dl, int32_t* __restrict__ target_ind, float* __restrict__ xref,
+                        const double DT) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float sx = state[i], sy = state[n + i], sv = state[3 * n + i];
@@ -854,7 +876,6 @@ crb_mpc_ref_traj_kernel(int64_t n, int T, const float* __restrict__ state,
   }
   int ind = (int)find;
   if (pind >= ind) ind = pind;  // :139
-  const double DT = 0.2;
   float travel = 0.0f;
   for (int t = 0; t < T; ++t) {
     travel = (float)((double)travel + (double)fabsf(sv) * DT);  // :149
@@ -877,11 +898,11 @@ extern "C" int crb_mpc_calc_ref_trajectory_batched(crb_ctx* ctx, int64_t n, int 
   CRB_REQUIRE(ctx != nullptr, "ctx is NULL");
   CRB_REQUIRE(n >= 0 && T >= 1 && T <= CRB_MPC_MAX_T, "n < 0 or T out of range");
   CRB_REQUIRE(ncourse >= 1 && dl > 0.0f, "empty course or dl <= 0");
-  (void)prm;
+  CRB_REQUIRE(prm != nullptr && prm->dt > 0.0f, "prm is NULL or dt <= 0");
   if (n == 0) return CRB_OK;
   CRB_REQUIRE(state && cx && cy && cyaw && sp && target_ind && xref, "NULL array");
   crb_mpc_ref_traj_kernel<<<crb_grid_for(n, 256), 256, 0, ctx->stream>>>(
-      n, T, state, cx, cy, cyaw, sp, ncourse, dl, target_ind, xref);
+      n, T, state, cx, cy, cyaw, sp, ncourse, dl, target_ind, xref, mpc_plant_constants(prm).dt);
   CRB_CUDA(cudaGetLastError());
   ctx->launches++;
   return CRB_OK;

@@ -22,16 +22,18 @@
 //   * Problems are pulled from a global counter 32 at a time, so the 148 CTAs balance themselves and the
 //     inputs of a refill are coalesced 128-byte rows of the SoA arrays.
 //
-// Scheduling state per CTA (shared memory): phase[S] (what each slot waits for), one lock word.  A warp
-// takes the lock (~150 cycles, once per ~10^4-cycle sweep), picks the kind with the most waiting slots,
-// marks up to 32 of them BUSY, releases.  Results are published with a block-scope fence before the
-// slot's new phase is stored.  All waiting loops are bounded: on overrun the kernel raises the error word
-// in the slab header instead of hanging the GPU.
+// Scheduling state per CTA (shared memory): one ring queue of waiting slots per sweep kind and one lock
+// word.  A warp enters ONE short critical section per task: it appends the slots of the sweep it just
+// finished to the queues of the kinds they wait for next, then takes up to 32 slots from the fullest
+// queue.  (The first version scanned a phase word per slot with 40 ballots under the lock: ncu showed 37 %
+// of all warp samples in that scan and in the lock's spin loop.)  Warps that find nothing wait on a
+// sequence word that every post bumps, not on the lock.  All waiting loops are bounded: on overrun the
+// kernel raises the error word in the slab header instead of hanging the GPU.
 #include "crb_common.cuh"
 #include "crb_mpc_core.cuh"
 #include "crb_mpc_tasks.cuh"
 
-#define MPC_TASK_MAX_CHUNKS 8  // S <= 256 slots
+#define MPC_TASK_QS 256  // ring size of the per-kind queues (power of two >= slots per CTA)
 
 struct MpcTaskArgs {
   int64_t count, ld_in, ld_out;
@@ -48,6 +50,17 @@ struct MpcTaskArgs {
   int32_t* iters;
 };
 
+// Scheduling state of one CTA (shared memory, after the slots).  Everything except `seq` is read and
+// written under `lock` only.
+struct MpcSched {
+  int q[3][MPC_TASK_QS];  // slots waiting for a REFILL / BW / FW sweep (ring buffers)
+  int head[3], tail[3];   // monotonic positions into q[k]
+  int inflight;           // warps that are executing a task
+  int lock;
+  int seq;                // bumped whenever work is posted: idle warps watch it instead of the lock
+  int pad;
+};
+
 __device__ __forceinline__ unsigned lanemask_lt() {
   unsigned m;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
@@ -58,81 +71,92 @@ __global__ void __launch_bounds__(MPC_TASK_MAX_WARPS * 32, 1)
 crb_mpc_tasks_kernel(const __grid_constant__ MpcTaskArgs A, const __grid_constant__ MpcP p) {
   extern __shared__ __align__(16) float smem[];
   const int S = A.S, T = A.T, N = T - 1, SW = A.slot_words;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int* phase = reinterpret_cast<int*>(smem + (size_t)S * SW);  // [MPC_TASK_MAX_CHUNKS * 32]
-  int* claim = phase + MPC_TASK_MAX_CHUNKS * 32;                // [MPC_TASK_MAX_WARPS][32]
-  int* lock = claim + MPC_TASK_MAX_WARPS * 32;
-  for (int s = threadIdx.x; s < MPC_TASK_MAX_CHUNKS * 32; s += blockDim.x)
-    phase[s] = s < S ? MPC_PH_REFILL : MPC_PH_DEAD;
-  for (int s = threadIdx.x; s < S; s += blockDim.x)
+  const int lane = threadIdx.x & 31;
+  MpcSched* const sc = reinterpret_cast<MpcSched*>(smem + (size_t)S * SW);
+  volatile int* const vhead = sc->head;
+  volatile int* const vtail = sc->tail;
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    sc->q[0][s] = s;  // every slot starts empty and waits for a refill
     reinterpret_cast<int*>(smem + (size_t)s * SW + mpc_slot_tr_words(T))[MPC_SW_PROB] = -1;
-  if (threadIdx.x == 0) *lock = 0;
+  }
+  if (threadIdx.x == 0) {
+    sc->head[0] = sc->head[1] = sc->head[2] = 0;
+    sc->tail[0] = S; sc->tail[1] = sc->tail[2] = 0;
+    sc->inflight = 0; sc->lock = 0; sc->seq = 0;
+  }
   __syncthreads();
   float* const slab = A.slab + (size_t)blockIdx.x * S * N * MPC_REC;
   const int tr_words = mpc_slot_tr_words(T);
   const unsigned FULL = 0xffffffffu;
-  int idle_spins = 0;
 
+  bool have_post = false, active = false;
+  int slot = 0, next = MPC_PH_DEAD;
   for (;;) {
-    // ---- claim: up to 32 slots waiting for the same kind of sweep ---------------------------------
+    // ---- one critical section per task: publish the finished sweep's slots, take the next batch -------
     int got = 1;
     if (lane == 0) {
       int tries = 0;
-      while (atomicCAS(lock, 0, 1) != 0) {
-        __nanosleep(64);
-        if (++tries > (1 << 22)) { atomicExch(&A.header[1], 1ull); got = 0; break; }
+      while (atomicCAS(&sc->lock, 0, 1) != 0) {
+        __nanosleep(32);
+        if (++tries > (1 << 24)) { atomicExch(&A.header[1], 1ull); got = 0; break; }
       }
     }
     got = __shfl_sync(FULL, got, 0);
     if (!got) break;  // never hang the GPU on a scheduling bug: raise the error word and leave
     __threadfence_block();
-    int ph[MPC_TASK_MAX_CHUNKS];
-    int cnt_refill = 0, cnt_bw = 0, cnt_fw = 0, cnt_busy = 0;
+    if (have_post) {
 #pragma unroll
-    for (int c = 0; c < MPC_TASK_MAX_CHUNKS; ++c) {
-      ph[c] = *reinterpret_cast<volatile int*>(phase + c * 32 + lane);
-      cnt_refill += __popc(__ballot_sync(FULL, ph[c] == MPC_PH_REFILL));
-      cnt_bw += __popc(__ballot_sync(FULL, ph[c] == MPC_PH_BW));
-      cnt_fw += __popc(__ballot_sync(FULL, ph[c] == MPC_PH_FW));
-      cnt_busy += __popc(__ballot_sync(FULL, ph[c] == MPC_PH_BUSY));
-    }
-    int kind = MPC_PH_FW, best = cnt_fw;
-    if (cnt_bw > best) { kind = MPC_PH_BW; best = cnt_bw; }
-    if (cnt_refill > best) { kind = MPC_PH_REFILL; best = cnt_refill; }
-    int taken = 0;
-    if (best > 0) {
-#pragma unroll
-      for (int c = 0; c < MPC_TASK_MAX_CHUNKS; ++c) {
-        const bool mine = ph[c] == kind;
+      for (int k = 0; k < 3; ++k) {
+        const bool mine = active && next == k + 1;
         const unsigned m = __ballot_sync(FULL, mine);
-        const int r = taken + __popc(m & lanemask_lt());
-        if (mine && r < 32) {
-          phase[c * 32 + lane] = MPC_PH_BUSY;
-          claim[warp * 32 + r] = c * 32 + lane;
+        if (m) {
+          const int base = vtail[k];
+          if (mine) sc->q[k][(base + __popc(m & lanemask_lt())) & (MPC_TASK_QS - 1)] = slot;
+          __syncwarp();
+          if (lane == 0) vtail[k] = base + __popc(m);
         }
-        taken += __popc(m);
       }
-      if (taken > 32) taken = 32;
+      if (lane == 0) {
+        *(volatile int*)&sc->inflight = *(volatile int*)&sc->inflight - 1;
+        *(volatile int*)&sc->seq = *(volatile int*)&sc->seq + 1;
+      }
+      __syncwarp();
+    }
+    const int h0 = vhead[0], h1 = vhead[1], h2 = vhead[2];
+    const int c_refill = vtail[0] - h0, c_bw = vtail[1] - h1, c_fw = vtail[2] - h2;
+    int kind = MPC_PH_FW, best = c_fw, hk = h2;
+    if (c_bw > best) { kind = MPC_PH_BW; best = c_bw; hk = h1; }
+    if (c_refill > best) { kind = MPC_PH_REFILL; best = c_refill; hk = h0; }
+    const int taken = best < 32 ? best : 32;
+    active = lane < taken;
+    slot = active ? *(volatile int*)&sc->q[kind - 1][(hk + lane) & (MPC_TASK_QS - 1)] : 0;
+    int infl = *(volatile int*)&sc->inflight;
+    const int seen = *(volatile int*)&sc->seq;
+    __syncwarp();
+    if (lane == 0 && taken > 0) {
+      vhead[kind - 1] = hk + taken;
+      *(volatile int*)&sc->inflight = infl + 1;
     }
     __threadfence_block();
     __syncwarp();
-    if (lane == 0) atomicExch(lock, 0);
-    if (best == 0) {
-      if (cnt_busy == 0) break;  // every slot is dead: this CTA is done
-      __nanosleep(256);
-      if (++idle_spins > (1 << 22)) { if (lane == 0) atomicExch(&A.header[1], 2ull); break; }
+    if (lane == 0) atomicExch(&sc->lock, 0);
+    have_post = false;
+    if (taken == 0) {
+      if (infl == 0) break;  // nothing waits and nobody is working: this CTA is done
+      int spins = 0;         // wait for the next post without touching the lock
+      while (*(volatile int*)&sc->seq == seen) {
+        __nanosleep(128);
+        if (++spins > (1 << 23)) { if (lane == 0) atomicExch(&A.header[1], 2ull); break; }
+      }
+      if (spins > (1 << 23)) break;
       continue;
     }
-    idle_spins = 0;
-    const bool active = lane < taken;
-    const int slot = active ? claim[warp * 32 + lane] : 0;
-    __syncwarp();
     MpcSlot sl;
     sl.tr = smem + (size_t)slot * SW;
     sl.sw = sl.tr + tr_words;
     sl.rec = slab + (size_t)slot * N * MPC_REC;
 
-    int next = MPC_PH_DEAD;
+    next = MPC_PH_DEAD;
     if (kind == MPC_PH_BW) {
       if (active) next = mpc_task_bw(sl, T, p);
     } else if (kind == MPC_PH_FW) {
@@ -150,14 +174,13 @@ crb_mpc_tasks_kernel(const __grid_constant__ MpcTaskArgs A, const __grid_constan
         if (i < A.count) {
           next = mpc_task_init(sl, T, p, i, A.ld_in, A.x0, A.xref, A.u_init);
         } else {
-          mpc_sw_int(sl, MPC_SW_PROB) = -1;
+          mpc_sw_int(sl, MPC_SW_PROB) = -1;  // the batch is exhausted: the slot stays empty
           next = MPC_PH_DEAD;
         }
       }
     }
-    // publish: data first, then the phase
-    __threadfence_block();
-    if (active) *reinterpret_cast<volatile int*>(phase + slot) = next;
+    __threadfence_block();  // the sweep's results are visible before the slots are queued again
+    have_post = true;
   }
 }
 
@@ -177,9 +200,9 @@ static bool mpc_tasks_geometry(int sm_count, int T, int64_t count, MpcTaskGeom* 
   }
   int nwarps = env_warps > 0 ? env_warps : MPC_TASK_MAX_WARPS;
   if (nwarps > MPC_TASK_MAX_WARPS) nwarps = MPC_TASK_MAX_WARPS;
-  const size_t fixed = (size_t)(MPC_TASK_MAX_CHUNKS * 32 + MPC_TASK_MAX_WARPS * 32 + 4) * sizeof(int);
+  const size_t fixed = sizeof(MpcSched);
   size_t s = (smem_cap - fixed) / ((size_t)mpc_slot_words(T) * sizeof(float));
-  if (s > MPC_TASK_MAX_CHUNKS * 32) s = MPC_TASK_MAX_CHUNKS * 32;
+  if (s > MPC_TASK_QS) s = MPC_TASK_QS;
   int S = (int)s;
   if (env_slots > 0 && env_slots < S) S = env_slots;
   if (S < 32) return false;

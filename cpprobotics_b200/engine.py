@@ -183,7 +183,7 @@ class Engine:
             self.ctx, n, _ptr(px, np.float32, device=True, name="px"), _ptr(pw, np.float32, device=True, name="pw"),
             _ptr(px_tmp, np.float32, device=True, name="px_tmp"),
             _ptr(uniforms, np.float32, device=True, name="uniforms"), C.c_uint64(int(seed)),
-            C.c_float(n / 2 if nth is None else nth), C.addressof(did), C.addressof(neff)), "crb_pf_resample")
+            C.c_float(n // 2 if nth is None else nth), C.addressof(did), C.addressof(neff)), "crb_pf_resample")
         return bool(did.value), neff.value
 
     # ---- MPC --------------------------------------------------------------------------------------

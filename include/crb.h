@@ -211,6 +211,10 @@ int crb_mpc_solve_batched_host(crb_ctx* ctx, int64_t n, int T, const float* x0, 
                                const float* u_init, const crb_mpc_params* prm, float* sol,
                                float* u0, float* cost, int32_t* status, int32_t* iters);
 /* Plant step on the first control: state [4][n] in/out, u0 [2][n] = (a, delta).
+ * Uses prm->max_steer, dt, wb, max_speed, min_speed (required, not NULL).  The reference evaluates this
+ * step in double because its constants are double macros (:26-38): a parameter equal to the reference's
+ * macro rounded to float is taken as the macro's double value (defaults are bit-identical to the
+ * reference), any other value is promoted from float.  The same rule gives calc_ref_trajectory its DT.
  * Replaces: update(State&, float a, float delta), src/model_predictive_control.cpp:69-81. */
 int crb_mpc_plant_update_batched(crb_ctx* ctx, int64_t n, float* state, const float* u0,
                                  const crb_mpc_params* prm);

@@ -66,19 +66,41 @@ inline void check(int rc, const char* what) {
                              "): " + crb_last_error_string());
 }
 
-// One lazily created context per thread (a crb_ctx is not thread-safe).
+// One lazily created context per thread (a crb_ctx is not thread-safe).  The session also owns a grow-only
+// device arena: the shims below carve their per-call device buffers out of it, so a reference main() that
+// calls update() / calc_ref_trajectory() every step does not pay cudaMalloc + cudaFree per call, and an
+// exception thrown between "allocate" and "free" cannot leak device memory (there is nothing to free).
 class Session {
  public:
-  static crb_ctx* get() {
-    thread_local Session s;
-    return s.ctx_;
+  static crb_ctx* get() { return self().ctx_; }
+  // at least n_floats floats of device memory, valid until the next scratch() call on this thread
+  static float* scratch(size_t n_floats) {
+    Session& s = self();
+    if (n_floats > s.cap_) {
+      if (s.arena_) crb_device_free(s.ctx_, s.arena_);
+      s.arena_ = nullptr;
+      s.cap_ = 0;
+      size_t want = n_floats < 4096 ? 4096 : n_floats;
+      check(crb_device_alloc(s.ctx_, &s.arena_, want * sizeof(float)), "crb_device_alloc");
+      s.cap_ = want;
+    }
+    return (float*)s.arena_;
   }
   Session(const Session&) = delete;
 
  private:
+  static Session& self() {
+    thread_local Session s;
+    return s;
+  }
   Session() { check(crb_init(&ctx_, -1), "crb_init"); }
-  ~Session() { crb_destroy(ctx_); }
+  ~Session() {
+    if (arena_) crb_device_free(ctx_, arena_);
+    crb_destroy(ctx_);
+  }
   crb_ctx* ctx_ = nullptr;
+  void* arena_ = nullptr;
+  size_t cap_ = 0;
 };
 
 }  // namespace crb
@@ -119,18 +141,14 @@ inline void ekf_estimation(crb::Vector4f& xEst, crb::Matrix4f& PEst, crb::Vector
 inline void update(cpprobotics::State& state, float a, float delta) {
   crb_ctx* ctx = crb::Session::get();
   float st[4] = {state.x, state.y, state.yaw, state.v}, u0[2] = {a, delta};
-  void *dst = nullptr, *du = nullptr;
-  crb::check(crb_device_alloc(ctx, &dst, sizeof(st)), "crb_device_alloc");
-  crb::check(crb_device_alloc(ctx, &du, sizeof(u0)), "crb_device_alloc");
+  float* dst = crb::Session::scratch(6);
+  float* du = dst + 4;
   crb::check(crb_memcpy_h2d(ctx, dst, st, sizeof(st)), "crb_memcpy_h2d");
   crb::check(crb_memcpy_h2d(ctx, du, u0, sizeof(u0)), "crb_memcpy_h2d");
   crb_mpc_params prm;
   crb_mpc_default_params(&prm);
-  crb::check(crb_mpc_plant_update_batched(ctx, 1, (float*)dst, (const float*)du, &prm),
-             "crb_mpc_plant_update_batched");
+  crb::check(crb_mpc_plant_update_batched(ctx, 1, dst, du, &prm), "crb_mpc_plant_update_batched");
   crb::check(crb_memcpy_d2h(ctx, st, dst, sizeof(st)), "crb_memcpy_d2h");
-  crb_device_free(ctx, dst);
-  crb_device_free(ctx, du);
   state.x = st[0]; state.y = st[1]; state.yaw = st[2]; state.v = st[3];
 }
 
@@ -166,12 +184,10 @@ inline void calc_ref_trajectory(cpprobotics::State state, cpprobotics::Vec_f cx,
   const size_t nc = cx.size();
   const float st[4] = {state.x, state.y, state.yaw, state.v};
   int32_t ti = target_ind;
-  void *dcourse = nullptr, *dst = nullptr, *dti = nullptr, *dxr = nullptr;
-  crb::check(crb_device_alloc(ctx, &dcourse, 4 * nc * sizeof(float)), "crb_device_alloc");
-  crb::check(crb_device_alloc(ctx, &dst, sizeof(st)), "crb_device_alloc");
-  crb::check(crb_device_alloc(ctx, &dti, sizeof(ti)), "crb_device_alloc");
-  crb::check(crb_device_alloc(ctx, &dxr, 4 * T * sizeof(float)), "crb_device_alloc");
-  float* dc = (float*)dcourse;
+  float* dc = crb::Session::scratch(4 * nc + 4 + 4 + 4 * T);   // course | state | target_ind | xref
+  float* dst = dc + 4 * nc;
+  float* dti = dst + 4;
+  float* dxr = dti + 4;
   crb::check(crb_memcpy_h2d(ctx, dc, cx.data(), nc * sizeof(float)), "h2d");
   crb::check(crb_memcpy_h2d(ctx, dc + nc, cy.data(), nc * sizeof(float)), "h2d");
   crb::check(crb_memcpy_h2d(ctx, dc + 2 * nc, cyaw.data(), nc * sizeof(float)), "h2d");
@@ -180,14 +196,11 @@ inline void calc_ref_trajectory(cpprobotics::State state, cpprobotics::Vec_f cx,
   crb::check(crb_memcpy_h2d(ctx, dti, &ti, sizeof(ti)), "h2d");
   crb_mpc_params prm;
   crb_mpc_default_params(&prm);
-  crb::check(crb_mpc_calc_ref_trajectory_batched(ctx, 1, T, (const float*)dst, dc, dc + nc,
-                                                 dc + 2 * nc, dc + 3 * nc, (int32_t)nc, dl,
-                                                 (int32_t*)dti, (float*)dxr, &prm),
+  crb::check(crb_mpc_calc_ref_trajectory_batched(ctx, 1, T, dst, dc, dc + nc, dc + 2 * nc, dc + 3 * nc,
+                                                 (int32_t)nc, dl, (int32_t*)dti, dxr, &prm),
              "crb_mpc_calc_ref_trajectory_batched");
   crb::check(crb_memcpy_d2h(ctx, xref.data(), dxr, 4 * T * sizeof(float)), "d2h");
   crb::check(crb_memcpy_d2h(ctx, &ti, dti, sizeof(ti)), "d2h");
-  crb_device_free(ctx, dcourse); crb_device_free(ctx, dst);
-  crb_device_free(ctx, dti); crb_device_free(ctx, dxr);
   target_ind = ti;
 }
 
@@ -217,24 +230,20 @@ inline void pf_localization(crb::Mat<4, NP>& px, crb::Mat<NP, 1>& pw, crb::Vecto
   }
   for (size_t i = 0; i < z.size(); ++i)
     for (int k = 0; k < 3; ++k) lm[3 * i + k] = z[i](0, k);
-  void *dpx = nullptr, *dpw = nullptr, *dn = nullptr;
-  crb::check(crb_device_alloc(ctx, &dpx, sx.size() * sizeof(float)), "crb_device_alloc");
-  crb::check(crb_device_alloc(ctx, &dpw, NP * sizeof(float)), "crb_device_alloc");
-  crb::check(crb_device_alloc(ctx, &dn, noise.size() * sizeof(float)), "crb_device_alloc");
+  float* dpx = crb::Session::scratch(7 * (size_t)NP);   // px [4][NP] | pw [NP] | noise [2][NP]
+  float* dpw = dpx + 4 * NP;
+  float* dn = dpw + NP;
   crb::check(crb_memcpy_h2d(ctx, dpx, sx.data(), sx.size() * sizeof(float)), "h2d");
   crb::check(crb_memcpy_h2d(ctx, dpw, pw.data(), NP * sizeof(float)), "h2d");
   crb::check(crb_memcpy_h2d(ctx, dn, noise.data(), noise.size() * sizeof(float)), "h2d");
-  crb::check(crb_pf_predict_weight_batched(ctx, NP, (float*)dpx, (float*)dpw, (const float*)dn, 0,
-                                           lm.data(), (int)z.size(), &prm),
+  crb::check(crb_pf_predict_weight_batched(ctx, NP, dpx, dpw, dn, 0, lm.data(), (int)z.size(), &prm),
              "crb_pf_predict_weight_batched");                          // :81-102
-  crb::check(crb_pf_estimate(ctx, NP, (const float*)dpx, (float*)dpw, xEst.data(), PEst.data(),
-                             nullptr),
+  crb::check(crb_pf_estimate(ctx, NP, dpx, dpw, xEst.data(), PEst.data(), nullptr),
              "crb_pf_estimate");                                        // :104-107
   crb::check(crb_memcpy_d2h(ctx, sx.data(), dpx, sx.size() * sizeof(float)), "d2h");
   crb::check(crb_memcpy_d2h(ctx, pw.data(), dpw, NP * sizeof(float)), "d2h");
   for (int ip = 0; ip < NP; ++ip)
     for (int k = 0; k < 4; ++k) px(k, ip) = sx[k * NP + ip];
-  crb_device_free(ctx, dpx); crb_device_free(ctx, dpw); crb_device_free(ctx, dn);
 }
 
 // src/particle_filter.cpp:120-148.  gen and uni_d BY VALUE like the reference (:122-123: the caller's
@@ -251,17 +260,16 @@ inline void resampling(crb::Mat<4, NP>& px, crb::Mat<NP, 1>& pw, std::mt19937 ge
     for (int k = 0; k < 4; ++k) sx[k * NP + ip] = px(k, ip);
     un[ip] = (float)uni_d(gen);
   }
-  void *dpx = nullptr, *dpw = nullptr, *dtmp = nullptr, *du = nullptr;
-  crb::check(crb_device_alloc(ctx, &dpx, sx.size() * sizeof(float)), "crb_device_alloc");
-  crb::check(crb_device_alloc(ctx, &dtmp, sx.size() * sizeof(float)), "crb_device_alloc");
-  crb::check(crb_device_alloc(ctx, &dpw, NP * sizeof(float)), "crb_device_alloc");
-  crb::check(crb_device_alloc(ctx, &du, NP * sizeof(float)), "crb_device_alloc");
+  float* dpx = crb::Session::scratch(10 * (size_t)NP);   // px [4][NP] | px_tmp [4][NP] | pw [NP] | uniforms [NP]
+  float* dtmp = dpx + 4 * NP;
+  float* dpw = dtmp + 4 * NP;
+  float* du = dpw + NP;
   crb::check(crb_memcpy_h2d(ctx, dpx, sx.data(), sx.size() * sizeof(float)), "h2d");
   crb::check(crb_memcpy_h2d(ctx, dpw, pw.data(), NP * sizeof(float)), "h2d");
   crb::check(crb_memcpy_h2d(ctx, du, un.data(), NP * sizeof(float)), "h2d");
   int did = 0;
-  crb::check(crb_pf_resample(ctx, NP, (float*)dpx, (float*)dpw, (float*)dtmp, (const float*)du, 0,
-                             (float)(NP / 2.0), &did, nullptr),
+  // NTh = NP / 2 is an INTEGER expression in the reference (:22)
+  crb::check(crb_pf_resample(ctx, NP, dpx, dpw, dtmp, du, 0, (float)(NP / 2), &did, nullptr),
              "crb_pf_resample");
   if (did) {
     crb::check(crb_memcpy_d2h(ctx, sx.data(), dpx, sx.size() * sizeof(float)), "d2h");
@@ -269,7 +277,6 @@ inline void resampling(crb::Mat<4, NP>& px, crb::Mat<NP, 1>& pw, std::mt19937 ge
     for (int ip = 0; ip < NP; ++ip)
       for (int k = 0; k < 4; ++k) px(k, ip) = sx[k * NP + ip];
   }
-  crb_device_free(ctx, dpx); crb_device_free(ctx, dtmp); crb_device_free(ctx, dpw); crb_device_free(ctx, du);
 }
 
 // solve_DARE + dlqr: src/lqr_steer_control.cpp:75-96 (nx = 4, scalar R) and
@@ -284,9 +291,7 @@ template <int NX, int NU>
 inline void dlqr_impl(const float* A, const float* B, const float* Q, const float* R, float* K, float* X) {
   crb_ctx* ctx = Session::get();
   const size_t na = NX * NX, nb = NX * NU, nr = NU * NU, nk = NU * NX;
-  void* d = nullptr;
-  check(crb_device_alloc(ctx, &d, (2 * na + nb + nr + nk + na) * sizeof(float)), "crb_device_alloc");
-  float* dA = (float*)d;
+  float* dA = Session::scratch(2 * na + nb + nr + nk + na);
   float *dB = dA + na, *dQ = dB + nb, *dR = dQ + na, *dK = dR + nr, *dX = dK + nk;
   check(crb_memcpy_h2d(ctx, dA, A, na * sizeof(float)), "h2d");
   check(crb_memcpy_h2d(ctx, dB, B, nb * sizeof(float)), "h2d");
@@ -297,7 +302,6 @@ inline void dlqr_impl(const float* A, const float* B, const float* Q, const floa
         "crb_lqr_dlqr_batched");
   if (K) check(crb_memcpy_d2h(ctx, K, dK, nk * sizeof(float)), "d2h");
   if (X) check(crb_memcpy_d2h(ctx, X, dX, na * sizeof(float)), "d2h");
-  crb_device_free(ctx, d);
 }
 }  // namespace crb
 
