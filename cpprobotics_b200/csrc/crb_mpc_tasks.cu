@@ -89,6 +89,11 @@ crb_mpc_tasks_kernel(const __grid_constant__ MpcTaskArgs A, const __grid_constan
   const int tr_words = mpc_slot_tr_words(T);
   const unsigned FULL = 0xffffffffu;
 
+  const unsigned long long pol = mpc_policy_evict_last();
+  // this warp's record ring (forward sweeps), after the scheduling state
+  const unsigned ring = (unsigned)__cvta_generic_to_shared(reinterpret_cast<char*>(sc + 1) +
+                                                           (size_t)(threadIdx.x >> 5) * MPC_RING_BYTES) +
+                        (unsigned)lane * 16u;
   bool have_post = false, active = false;
   int slot = 0, next = MPC_PH_DEAD;
   for (;;) {
@@ -155,6 +160,8 @@ crb_mpc_tasks_kernel(const __grid_constant__ MpcTaskArgs A, const __grid_constan
     sl.tr = smem + (size_t)slot * SW;
     sl.sw = sl.tr + tr_words;
     sl.rec = slab + (size_t)slot * N * MPC_REC;
+    sl.pol = pol;
+    sl.ring = ring;
 
     next = MPC_PH_DEAD;
     if (kind == MPC_PH_BW) {
@@ -200,14 +207,20 @@ static bool mpc_tasks_geometry(int sm_count, int T, int64_t count, MpcTaskGeom* 
   }
   int nwarps = env_warps > 0 ? env_warps : MPC_TASK_MAX_WARPS;
   if (nwarps > MPC_TASK_MAX_WARPS) nwarps = MPC_TASK_MAX_WARPS;
-  const size_t fixed = sizeof(MpcSched);
-  size_t s = (smem_cap - fixed) / ((size_t)mpc_slot_words(T) * sizeof(float));
-  if (s > MPC_TASK_QS) s = MPC_TASK_QS;
-  int S = (int)s;
-  if (env_slots > 0 && env_slots < S) S = env_slots;
+  // shared memory: slots, scheduling state, one record ring per warp.  Fewer warps leave more slots waiting
+  // (fuller warps of one kind); the default takes the most warps that keep >= 24 slots waiting.
+  int S = 0;
+  size_t fixed = 0;
+  for (;; --nwarps) {
+    fixed = sizeof(MpcSched) + (size_t)nwarps * MPC_RING_BYTES;
+    size_t s = (smem_cap - fixed) / ((size_t)mpc_slot_words(T) * sizeof(float));
+    if (s > MPC_TASK_QS) s = MPC_TASK_QS;
+    S = (int)s;
+    if (env_slots > 0 && env_slots < S) S = env_slots;
+    if (nwarps == 1) break;
+    if (env_warps > 0 ? nwarps * 32 <= S : nwarps * 32 + 24 <= S) break;
+  }
   if (S < 32) return false;
-  // as many warps as leave ~40 slots waiting, so that full warps of one kind can form
-  while (nwarps > 1 && nwarps * 32 + 40 > S) --nwarps;
   // one CTA per SM; fewer when the batch has less than one task per warp
   int64_t grid = (count + (int64_t)nwarps * 32 - 1) / ((int64_t)nwarps * 32);
   if (grid > sm_count) grid = sm_count;

@@ -58,6 +58,8 @@ extern "C" int mpc_tasks_sim_solve(int64_t n, int T, const float* x0, const floa
     sl.tr = smem + (size_t)s * SW;
     sl.sw = sl.tr + trw;
     sl.rec = slab + (size_t)s * N * MPC_REC;
+    sl.pol = 0;
+    sl.ring = 0;
     return sl;
   };
   for (int s = 0; s < S; ++s) mpc_sw_int(slot_of(s), MPC_SW_PROB) = -1;
