@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libcrb.so")
 CRB_OK = 0
 CRB_ERR_NO_DEVICE = -2
 CRB_STATS_LEN = 8
+CRB_COMM_ID_BYTES = 128
 CRB_PF_MAX_LANDMARKS = 64
 CRB_MPC_MAX_T = 32
 
@@ -94,6 +95,14 @@ PROTOTYPES = {
                                        C.c_void_p]),
     "crb_stats_reduce": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p]),
+    "crb_comm_nccl_version": (C.c_int, []),
+    "crb_comm_get_unique_id": (C.c_int, [C.c_void_p]),
+    "crb_comm_init_rank": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "crb_comm_destroy": (C.c_int, [C.c_void_p]),
+    "crb_comm_world": (C.c_int, [C.c_void_p]),
+    "crb_comm_rank": (C.c_int, [C.c_void_p]),
+    "crb_gather_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "crb_comm_allreduce_sum_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
 }
 
 _lib = None

@@ -31,7 +31,34 @@ struct crb_ctx {
   // per-device function attributes already set for this context's device (a second context on another
   // device in the same process must set them again, so these are not process-global latches)
   int mpc_tasks_attr_set;
+  int ekf_tma_attr_set;
+  int mpc_v0_attr_set;
+  // NCCL communicator (crb_comm.cu); NULL = single GPU
+  void* comm;
+  int comm_world, comm_rank;
 };
+
+// Makes ctx->device current for the duration of an entry point and restores the caller's device afterwards:
+// a process may hold contexts on several devices (one host thread each), and the caller's (torch's) current
+// device must not change under it.
+struct CrbDeviceGuard {
+  int prev;
+  bool ok;
+  explicit CrbDeviceGuard(const crb_ctx* ctx) : prev(-1), ok(true) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+    if (prev != ctx->device) ok = cudaSetDevice(ctx->device) == cudaSuccess;
+    else prev = -1;
+  }
+  ~CrbDeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+#define CRB_DEVICE_GUARD(ctx)                                            \
+  CrbDeviceGuard crb_guard_(ctx);                                        \
+  if (!crb_guard_.ok) {                                                  \
+    crb_set_error("%s: cudaSetDevice(%d) failed", __func__, (ctx)->device); \
+    return CRB_ERR_CUDA;                                                 \
+  }
 
 void crb_set_error(const char* fmt, ...);
 
@@ -56,6 +83,7 @@ void crb_set_error(const char* fmt, ...);
 int crb_ctx_pipe_reserve(crb_ctx* ctx, int slot, size_t bytes);
 int crb_ctx_scratch_reserve(crb_ctx* ctx, size_t bytes);
 int crb_ctx_mpc_ws_reserve(crb_ctx* ctx, size_t bytes);
+extern "C" int crb_comm_destroy(crb_ctx* ctx);
 
 // Strided host<->device block copy for the *_host pipelines.  Measured on this platform
 // (scripts/pcie_probe.py + bench e2e): plain 1-D copies reach 48 (H2D) / 57 (D2H) GB/s, one

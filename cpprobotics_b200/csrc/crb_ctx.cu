@@ -27,9 +27,10 @@ int crb_init(crb_ctx** out, int device_id) {
                   e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
     return CRB_ERR_NO_DEVICE;
   }
-  if (device_id < 0) CRB_CUDA(cudaGetDevice(&device_id));
+  int prev = -1;
+  CRB_CUDA(cudaGetDevice(&prev));
+  if (device_id < 0) device_id = prev;
   CRB_REQUIRE(device_id < count, "device_id out of range");
-  CRB_CUDA(cudaSetDevice(device_id));
   cudaDeviceProp prop;
   CRB_CUDA(cudaGetDeviceProperties(&prop, device_id));
   if (prop.major != 10) {
@@ -41,33 +42,51 @@ int crb_init(crb_ctx** out, int device_id) {
   memset(c, 0, sizeof(*c));
   c->device = device_id;
   c->sm_count = prop.multiProcessorCount;
-  CRB_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  c->comm_world = 1;
+  // everything below runs with device_id current; the caller's current device is restored on every path and a
+  // partially built context is torn down instead of leaked
+  cudaError_t err = cudaSetDevice(device_id);
+  if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
   c->stream = c->own_stream;
-  CRB_CUDA(cudaEventCreate(&c->ev_start));
-  CRB_CUDA(cudaEventCreate(&c->ev_stop));
-  for (int i = 0; i < CRB_N_PIPE; ++i)
-    CRB_CUDA(cudaStreamCreateWithFlags(&c->pipe_stream[i], cudaStreamNonBlocking));
-  CRB_CUDA(cudaMallocHost(&c->host_scratch, 4096));
+  if (err == cudaSuccess) err = cudaEventCreate(&c->ev_start);
+  if (err == cudaSuccess) err = cudaEventCreate(&c->ev_stop);
+  for (int i = 0; i < CRB_N_PIPE && err == cudaSuccess; ++i)
+    err = cudaStreamCreateWithFlags(&c->pipe_stream[i], cudaStreamNonBlocking);
+  if (err == cudaSuccess) err = cudaMallocHost(&c->host_scratch, 4096);
+  if (err != cudaSuccess) {
+    crb_set_error("crb_init: %s", cudaGetErrorString(err));
+    crb_destroy(c);
+    if (prev >= 0) cudaSetDevice(prev);
+    return err == cudaErrorMemoryAllocation ? CRB_ERR_ALLOC : CRB_ERR_CUDA;
+  }
+  if (prev >= 0 && prev != device_id) cudaSetDevice(prev);
   *out = c;
   return CRB_OK;
 }
 
 int crb_destroy(crb_ctx* ctx) {
   if (!ctx) return CRB_OK;
+  int prev = -1;
+  if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
-  cudaStreamSynchronize(ctx->own_stream);
+  if (ctx->comm) crb_comm_destroy(ctx);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
   for (int i = 0; i < CRB_N_PIPE; ++i) {
-    cudaStreamSynchronize(ctx->pipe_stream[i]);
+    if (ctx->pipe_stream[i]) {
+      cudaStreamSynchronize(ctx->pipe_stream[i]);
+      cudaStreamDestroy(ctx->pipe_stream[i]);
+    }
     if (ctx->pipe_buf[i]) cudaFree(ctx->pipe_buf[i]);
-    cudaStreamDestroy(ctx->pipe_stream[i]);
   }
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->mpc_ws) cudaFree(ctx->mpc_ws);
   if (ctx->host_scratch) cudaFreeHost(ctx->host_scratch);
-  cudaEventDestroy(ctx->ev_start);
-  cudaEventDestroy(ctx->ev_stop);
-  cudaStreamDestroy(ctx->own_stream);
+  if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+  if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  cudaGetLastError();
+  if (prev >= 0 && prev != ctx->device) cudaSetDevice(prev);
   delete ctx;
   return CRB_OK;
 }
@@ -102,12 +121,13 @@ int crb_host_free(void* p) {
 }
 int crb_device_alloc(crb_ctx* ctx, void** out, size_t bytes) {
   CRB_REQUIRE(ctx != nullptr && out != nullptr, "ctx/out is NULL");
-  CRB_CUDA(cudaSetDevice(ctx->device));
+  CRB_DEVICE_GUARD(ctx);
   CRB_CUDA(cudaMalloc(out, bytes ? bytes : 1));
   return CRB_OK;
 }
 int crb_device_free(crb_ctx* ctx, void* p) {
   CRB_REQUIRE(ctx != nullptr, "ctx is NULL");
+  CRB_DEVICE_GUARD(ctx);
   if (p) CRB_CUDA(cudaFree(p));
   return CRB_OK;
 }
@@ -187,6 +207,7 @@ void crb_mpc_default_params(crb_mpc_params* p) {
 }  // extern "C"
 
 int crb_ctx_pipe_reserve(crb_ctx* ctx, int slot, size_t bytes) {
+  CRB_DEVICE_GUARD(ctx);
   if (ctx->pipe_cap[slot] >= bytes) return CRB_OK;
   if (ctx->pipe_buf[slot]) {
     CRB_CUDA(cudaStreamSynchronize(ctx->pipe_stream[slot]));
@@ -200,6 +221,7 @@ int crb_ctx_pipe_reserve(crb_ctx* ctx, int slot, size_t bytes) {
 }
 
 int crb_ctx_scratch_reserve(crb_ctx* ctx, size_t bytes) {
+  CRB_DEVICE_GUARD(ctx);
   if (ctx->scratch_cap >= bytes) return CRB_OK;
   if (ctx->scratch) {
     CRB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -213,6 +235,7 @@ int crb_ctx_scratch_reserve(crb_ctx* ctx, size_t bytes) {
 }
 
 int crb_ctx_mpc_ws_reserve(crb_ctx* ctx, size_t bytes) {
+  CRB_DEVICE_GUARD(ctx);
   if (ctx->mpc_ws_cap >= bytes) return CRB_OK;
   if (ctx->mpc_ws) {
     CRB_CUDA(cudaStreamSynchronize(ctx->stream));

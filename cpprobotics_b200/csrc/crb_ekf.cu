@@ -276,12 +276,14 @@ template <int TILE, int STAGES>
 static int ekf_tma_launch(crb_ctx* ctx, cudaStream_t st, int64_t count, int64_t ld, float* x,
                           float* P, const float* z, const float* u, int64_t ld_zu,
                           const EkfArgs& a) {
-  static bool attr_set = false;
+  // per-context latch (bit per instantiation): the attribute is per device, and a process may hold contexts
+  // on several devices
   const size_t smem = ekf_tma_smem_bytes(TILE, STAGES);
-  if (!attr_set) {
+  const int bit = 1 << ((TILE == 256 ? 2 : 0) + (STAGES == 3 ? 1 : 0));
+  if (!(ctx->ekf_tma_attr_set & bit)) {
     CRB_CUDA(cudaFuncSetAttribute(crb_ekf_step_tma_kernel<TILE, STAGES>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    ctx->ekf_tma_attr_set |= bit;
   }
   const int64_t ntiles = (count + TILE - 1) / TILE;
   int per_sm = (int)((size_t)227 * 1024 / (smem + 1024));

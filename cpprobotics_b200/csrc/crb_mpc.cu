@@ -646,8 +646,10 @@ static int mpc_launch(crb_ctx* ctx, cudaStream_t st, int64_t count, int64_t ld, 
     const char* e = getenv("CRB_MPC_CTAS_PER_SM");
     const int k = e ? atoi(e) : 0;
     smem_cap = (k >= 1 && k <= 3) ? (int)((227 * 1024) / k - 2048) : 0;
-    if (smem_cap > 0)
-      cudaFuncSetAttribute(crb_mpc_solve_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap);
+  }
+  if (smem_cap > 0 && !ctx->mpc_v0_attr_set) {  // per context: the attribute belongs to the device
+    cudaFuncSetAttribute(crb_mpc_solve_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap);
+    ctx->mpc_v0_attr_set = 1;
   }
   cfg.dynamicSmemBytes = (size_t)smem_cap;
   cudaLaunchAttribute attr[1];

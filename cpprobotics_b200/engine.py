@@ -260,6 +260,44 @@ class Engine:
             _ptr(iters, np.int32, device=True, name="iters")), "crb_lqr_dlqr_batched")
         return K
 
+    # ---- multi-GPU: the communicator lives in libcrb (crb_comm.cu), not in torch --------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """Rank 0 calls this and hands the bytes to every rank (any channel: a store, MPI, a socket)."""
+        buf = C.create_string_buffer(_lib.CRB_COMM_ID_BYTES)
+        check(load_library().crb_comm_get_unique_id(buf), "crb_comm_get_unique_id")
+        return buf.raw
+
+    def comm_init(self, world: int, rank: int, unique_id: bytes) -> None:
+        """Collective: every rank of the job calls it with the same unique_id."""
+        if len(unique_id) != _lib.CRB_COMM_ID_BYTES:
+            raise ValueError("unique_id must be CRB_COMM_ID_BYTES long")
+        buf = C.create_string_buffer(unique_id, _lib.CRB_COMM_ID_BYTES)
+        check(self.lib.crb_comm_init_rank(self.ctx, int(world), int(rank), buf), "crb_comm_init_rank")
+
+    @property
+    def world(self) -> int:
+        return int(self.lib.crb_comm_world(self.ctx))
+
+    @property
+    def rank(self) -> int:
+        return int(self.lib.crb_comm_rank(self.ctx))
+
+    def gather_stats(self, stats, out=None):
+        """All-gather of CRB_STATS_LEN doubles per rank on the engine's stream -> [world, CRB_STATS_LEN]."""
+        w = self.world
+        if out is None:
+            out = torch.empty((w, _lib.CRB_STATS_LEN), dtype=torch.float64, device=stats.device)
+        check(self.lib.crb_gather_stats(self.ctx, _ptr(stats, np.float64, device=True, name="stats"),
+                                        _ptr(out, np.float64, device=True, name="out")), "crb_gather_stats")
+        return out
+
+    def allreduce_sum(self, buf):
+        """In-place sum over ranks of a float64 CUDA tensor (no-op without a communicator)."""
+        check(self.lib.crb_comm_allreduce_sum_f64(self.ctx, _ptr(buf, np.float64, device=True, name="buf"),
+                                                  int(buf.numel())), "crb_comm_allreduce_sum_f64")
+        return buf
+
     # ---- stats ------------------------------------------------------------------------------------
     def stats_reduce(self, values, status=None, iters=None, i0: int = 0, out=None):
         """Per-GPU summary of a per-agent f32 array -> float64 CUDA tensor of CRB_STATS_LEN."""

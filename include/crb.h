@@ -52,7 +52,7 @@
 extern "C" {
 #endif
 
-#define CRB_ABI_VERSION 1
+#define CRB_ABI_VERSION 2
 
 typedef enum crb_status {
   CRB_OK = 0,
@@ -242,6 +242,27 @@ int crb_lqr_dlqr_batched(crb_ctx* ctx, int64_t n, int nx, int nu, const float* A
                          const float* Q, const float* R, int maxiter, float eps, float* K, float* X,
                          int32_t* iters);
 
+/* ---- multi-GPU: communicator owned by the context (NCCL, opened at run time) ---------------------- */
+/* The batch shards over GPUs by contiguous agent ranges (one crb_ctx per device, one host thread or process
+ * each); the only inter-GPU traffic is crb_gather_stats (one all-gather of CRB_STATS_LEN doubles per rank)
+ * and, for a sharded particle filter, the all-reduce inside crb_pf_estimate.  Bootstrap like any NCCL
+ * program: rank 0 calls crb_comm_get_unique_id, the CRB_COMM_ID_BYTES bytes travel to every rank by the
+ * host's own channel, every rank calls crb_comm_init_rank (collectively).  libnccl is dlopen'ed on first use
+ * ($CRB_NCCL_LIB, then "libnccl.so.2"); CRB_ERR_UNSUPPORTED when it cannot be found.  A context without a
+ * communicator behaves as world = 1. */
+#define CRB_COMM_ID_BYTES 128
+int crb_comm_nccl_version(void);   /* e.g. 22809; 0 when no NCCL library could be opened */
+int crb_comm_get_unique_id(void* id_out /* CRB_COMM_ID_BYTES bytes */);
+int crb_comm_init_rank(crb_ctx* ctx, int world, int rank, const void* id);
+int crb_comm_destroy(crb_ctx* ctx);  /* also done by crb_destroy */
+int crb_comm_world(crb_ctx* ctx);
+int crb_comm_rank(crb_ctx* ctx);
+/* all_dev [world][CRB_STATS_LEN] (device, f64) <- every rank's stats_dev [CRB_STATS_LEN], enqueued on the
+ * context's stream (capturable in a CUDA graph).  SURVEY §8 b-4: "wraps the NCCL all-gather". */
+int crb_gather_stats(crb_ctx* ctx, const double* stats_dev, double* all_dev);
+/* In-place sum over ranks of `count` doubles on the device (the PF weight / moment sums). */
+int crb_comm_allreduce_sum_f64(crb_ctx* ctx, double* buf_dev, int64_t count);
+
 /* ---- summary statistics (the only inter-GPU payload) ------------------------------------------- */
 #define CRB_STATS_LEN 8
 /* Reduces a per-agent f32 array (and optional status / iteration arrays) on the device into
@@ -249,7 +270,7 @@ int crb_lqr_dlqr_batched(crb_ctx* ctx, int64_t n, int nx, int nu, const float* A
  *   [0] sum  [1] min  [2] max  [3] n_nonfinite  [4] n_status_converged  [5] sum_iters
  *   [6] position-weighted checksum  sum_i value_i * ((i0+i) % 251 + 1)  [7] n
  * i0 is the global index of this shard's first agent so that the checksum of a sharded run equals
- * the single-GPU one.  The caller all-gathers the 8 doubles across ranks (NCCL). */
+ * the single-GPU one.  crb_gather_stats all-gathers the 8 doubles across ranks. */
 int crb_stats_reduce(crb_ctx* ctx, int64_t n, int64_t i0, const float* values,
                      const int32_t* status, const int32_t* iters, double* stats_dev);
 

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load_library()
     for name in declared_symbols():
         assert hasattr(lib, name), name
-    assert lib.crb_abi_version() == 1
+    assert lib.crb_abi_version() == 2
 
 
 def test_struct_layouts_match_the_header(tmp_path):
