@@ -163,3 +163,57 @@ static inline int crb_grid_for(int64_t n, int block) { return (int)((n + block -
 // Streaming (evict-first) global accesses for data that is touched exactly once per launch.
 __device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
 __device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
+
+// ---- sin/cos with the HOST libm's bits ------------------------------------------------------------------
+// The reference calls std::sin / std::cos on floats (src/extended_kalman_filter.cpp:29-33,41-45,
+// src/particle_filter.cpp:33-37, src/model_predictive_control.cpp:73-74), i.e. glibc's sinf / cosf.  Those
+// are specified only to ~1 ulp, and one ulp of a predicted position is 3e-5 of a particle weight
+// (exp(-dz^2 / 2 sigma^2) with sigma = 0.1 m and ranges of ~15 m), so CUDA's own sincosf (also <= 2 ulp, but
+// different ulps) cannot meet a per-particle 1e-5 gate on the weights.  glibc >= 2.28 computes sinf / cosf
+// in BINARY64: x = (double)y, one multiply-subtract range reduction by pi/2 (exact to 33 bits for |y| < 120),
+// a degree-7/8 polynomial, one final rounding to float (sysdeps/ieee754/flt-32/s_sinf.c, s_cosf.c,
+// sincosf.h, s_sincosf_data.c).  Every operation is an IEEE binary64 multiply or add, which the B200's FP64
+// pipe reproduces bit for bit (this TU is built -fmad=false), so the routine below returns the host's bits:
+// checked against the host libm on 3.2e8 floats in |y| < 120 (oracle/crb_oracle.c:crb_oracle_libm_sincosf,
+// tests/test_oracle_ekf.py): sin identical, cos differs on 2e-8 of the inputs where glibc's FMA build
+// (ifunc-selected on hosts with FMA) rounds an intermediate differently.  |y| >= 120 (glibc's table-driven
+// reduce_large) is not restated: CUDA's sincosf is used there (no BASELINE workload comes near it).
+__device__ __forceinline__ void crb_sincosf_libm(float y, float& sn, float& cs) {
+  const unsigned top = (__float_as_uint(y) >> 20) & 0x7ffu;
+  if (top >= 0x42fu) {  // |y| >= 120, inf, nan
+    sincosf(y, &sn, &cs);
+    return;
+  }
+  double x = (double)y;
+  int n = 0;
+  double sgn = 1.0;
+  if (top >= 0x3f4u) {  // |y| >= pi/4 (abstop12(0x1.921FB6p-1f) = 0x3f4): reduce_fast
+    const double r = x * 0x1.45F306DC9C883p+23;
+    n = ((int)r + 0x800000) >> 24;
+    x = x - (double)n * 0x1.921FB54442D18p0;
+    sgn = ((n + 1) & 2) ? -1.0 : 1.0;  // sign[n & 3] = {1, -1, -1, 1}
+  } else if (top < 0x398u) {  // |y| < 2^-12
+    sn = y;
+    cs = 1.0f;
+    return;
+  }
+  const double x2 = x * x;
+  const double q = (n & 2) ? -1.0 : 1.0;  // second table entry: cosine coefficients negated
+  const double xs = x * sgn;
+  // sine polynomial on xs (its coefficients are the same in both table entries)
+  const double x3 = xs * x2;
+  const double s1 = 0x1.1107605230bc4p-7 + x2 * -0x1.994eb3774cf24p-13;
+  const double x7 = x3 * x2;
+  const double sp = xs + x3 * -0x1.555545995a603p-3;
+  const float ps = (float)(sp + x7 * s1);
+  // cosine polynomial
+  const double x4 = x2 * x2;
+  const double c2 = q * -0x1.6c087e89a359dp-10 + x2 * (q * 0x1.99343027bf8c3p-16);
+  const double c1 = q * 0x1p0 + x2 * (q * -0x1.ffffffd0c621cp-2);
+  const double x6 = x4 * x2;
+  const double cp = c1 + x4 * (q * 0x1.55553e1068f19p-5);
+  const float pc = (float)(cp + x6 * c2);
+  // sinf uses the sine polynomial for even n, cosf for odd n (and vice versa)
+  sn = (n & 1) ? pc : ps;
+  cs = (n & 1) ? ps : pc;
+}

@@ -15,7 +15,8 @@
 // an exact 0 is exact in IEEE arithmetic, so only the non-trivial terms are evaluated, in the same
 // (sequential-k) order and with separate multiply and add (this TU is compiled with -fmad=false; the
 // kernel is memory-bound, FMUL+FADD instead of FFMA costs nothing).  With that, results differ from
-// the CPU restatement only through sinf/cosf (CUDA vs glibc, <= 2 ulp).
+// the CPU restatement only where glibc's FMA build of sinf/cosf rounds differently from the plain binary64
+// evaluation in crb_sincosf_libm (2e-8 of the inputs).
 #include <stdint.h>
 #include <stdlib.h>
 
@@ -32,7 +33,7 @@ __device__ __forceinline__ void ekf_step(float (&x)[4], float (&P)[16], float z0
                                          float u0, float u1, const EkfArgs& a) {
   // ---- motion_model(xEst, u) :22-36.  B_(0,0) = DT*cos(yaw) is a double product narrowed to float.
   float s, c;
-  sincosf(x[2], &s, &c);
+  crb_sincosf_libm(x[2], s, c);   // the host libm's bits (crb_common.cuh)
   const float b00 = (float)(a.dt * (double)c);
   const float b10 = (float)(a.dt * (double)s);
   const float b21 = (float)a.dt;
@@ -44,7 +45,7 @@ __device__ __forceinline__ void ekf_step(float (&x)[4], float (&P)[16], float z0
 
   // ---- jacobF(xPred, u) :38-47: evaluated at the PREDICTED yaw with v = u(0).
   float s2, c2;
-  sincosf(xp[2], &s2, &c2);
+  crb_sincosf_libm(xp[2], s2, c2);
   const float j02 = (float)((-a.dt * (double)u0) * (double)s2);
   const float j03 = (float)(a.dt * (double)c2);
   const float j12 = (float)((a.dt * (double)u0) * (double)c2);

@@ -831,8 +831,10 @@ crb_mpc_plant_update_kernel(int64_t n, float* __restrict__ state, const float* _
   if ((double)delta >= MAX_STEER) delta = (float)MAX_STEER;
   if ((double)delta <= -MAX_STEER) delta = (float)(-MAX_STEER);
   const float x = state[i], y = state[n + i], yaw = state[2 * n + i], v = state[3 * n + i];
-  const float nx = (float)((double)x + (double)(v * cosf(yaw)) * DT);
-  const float ny = (float)((double)y + (double)(v * sinf(yaw)) * DT);
+  float sy, cy;
+  crb_sincosf_libm(yaw, sy, cy);   // std::cos / std::sin of a float: the host libm's bits (crb_common.cuh)
+  const float nx = (float)((double)x + (double)(v * cy) * DT);
+  const float ny = (float)((double)y + (double)(v * sy) * DT);
   const float nyaw = (float)((double)yaw + (double)v / WB * (double)tanf(delta) * DT);
   float nv = (float)((double)v + (double)a * DT);
   if ((double)nv > MAX_SPEED) nv = (float)MAX_SPEED;

@@ -73,6 +73,9 @@ int crb_oracle_num_threads(void);
 int64_t crb_oracle_check_const_division(float d, uint32_t lo_bits, uint32_t hi_bits);
 int64_t crb_oracle_check_ff_product(double pre, uint32_t lo_bits, uint32_t hi_bits);
 
+/* glibc's sinf / cosf restated (binary64 polynomial, what the kernels' crb_sincosf_libm executes) */
+void crb_oracle_libm_sincosf(float y, float* sn, float* cs);
+void crb_oracle_libm_sincosf_census(uint32_t lo_bits, uint32_t hi_bits, uint32_t step, int64_t* out);
 #ifdef __cplusplus
 }
 #endif

@@ -30,9 +30,14 @@ def test_ekf_device_matches_oracle(engine, n, steps):
     engine.ekf_estimation(xd, Pd, zd, ud, n_steps=steps)
     torch.cuda.synchronize()
     xo, Po = O.ekf_step_batched(x, P, z, u, n_steps=steps)
-    tol = 1e-5 if steps < 100 else 1e-4   # sinf/cosf ulp differences compound over 1000 steps
+    tol = 1e-5 if steps < 100 else 1e-4   # a 1-ulp sin/cos difference (glibc's FMA build) compounds over 1000 steps
     assert field_err(xd.cpu().numpy(), xo) <= tol
     assert field_err(Pd.cpu().numpy(), Po) <= tol
+    # sin/cos carry the host libm's bits (crb_sincosf_libm) and every other operation follows the oracle's
+    # order: a one-step update is IDENTICAL to the oracle for all but a handful of agents
+    if steps == 1:
+        same = (xd.cpu().numpy() == xo).all(axis=0) & (Pd.cpu().numpy() == Po).all(axis=0)
+        assert (~same).sum() <= max(1, int(4e-6 * n)), int((~same).sum())
 
 
 def test_ekf_host_entry_matches_device_entry_bitwise(engine):
@@ -80,24 +85,39 @@ def test_pf_device_matches_oracle(engine, n, n_lm):
     engine.pf_predict_weight(pxd, pwd, nd, lm)
     torch.cuda.synchronize()
     pxo, pwo = O.pf_predict_weight_batched(px, pw, noise, lm)
-    assert np.abs(pxd.cpu().numpy() - pxo).max() <= 1e-5 * max(1.0, np.abs(pxo).max())
-    _assert_weights_close(pwd.cpu().numpy(), pwo, pxo, lm)
+    _assert_pf_parity(pxd.cpu().numpy(), pwd.cpu().numpy(), pxo, pwo, lm)
 
 
-def _assert_weights_close(got, want, px_after, lm, sigma2=0.01):
-    """The likelihood exp(-dz^2 / 2 sigma^2) with sigma = 0.1 m and ranges of ~15 m amplifies one ulp of
-    the predicted position (|d prez| ~ 1e-6 m, from CUDA-vs-glibc sinf/cosf) to |dz|/sigma^2 * 1e-6 ~ 3e-5
-    relative PER LANDMARK, so a flat 1e-5 gate on w is not attainable by ANY two libms.  The gate is
-    therefore: field-normalised 1e-5  +  the weight's own condition number times 4 position ulps."""
-    cond = np.zeros(px_after.shape[1])
-    ulp = 0.0
-    for r, lx, ly in lm:
-        prez = np.hypot(px_after[0].astype(np.float64) - lx, px_after[1].astype(np.float64) - ly)
-        cond += np.abs(prez - r) / sigma2
-        ulp = max(ulp, float(np.spacing(np.float32(prez.max()))))
-    tol = 1e-5 * np.abs(want).max() + np.abs(want) * (cond * 4 * ulp + 32 * 2.0 ** -23)
-    bad = np.abs(got.astype(np.float64) - want) > tol
-    assert not bad.any(), (int(bad.sum()), float(np.abs(got - want).max()))
+def _assert_pf_parity(px_got, pw_got, px_want, pw_want, lm, sigma2=0.01):
+    """SURVEY §8 d-8 for the particle filter, as written: per-particle relative 1e-5 on w.
+
+    The kernels evaluate sin/cos with glibc's own binary64 algorithm (crb_sincosf_libm), so the predicted
+    positions carry the HOST libm's bits: they must be IDENTICAL to the oracle's, except on the ~2e-8 of the
+    arguments where glibc's FMA build rounds an intermediate differently (then 1 ulp).  On every particle with
+    identical positions the weight must agree to 1e-5 RELATIVE (w > 1e-30; the kernel's single fused
+    exponential differs from the reference's eight rounded factors by <= ~1e-6).  The few particles whose
+    position is an ulp off get the condition-number gate (one ulp of position is 3e-5 of w per landmark)."""
+    same = (px_got == px_want).all(axis=0)
+    n = same.size
+    n_off = int((~same).sum())
+    assert n_off <= max(2, int(4e-6 * n)), f"{n_off} of {n} predicted positions differ from the host libm path"
+    assert np.abs(px_got - px_want).max() <= 1e-6 * max(1.0, np.abs(px_want).max())
+    big = same & (pw_want > 1e-30)
+    rel = np.abs(pw_got[big].astype(np.float64) - pw_want[big]) / pw_want[big]
+    assert rel.size == 0 or rel.max() <= 1e-5, float(rel.max())
+    # underflow region: the reference's running product goes denormal / 0, the kernel floors exp at 2^-126
+    small = same & ~(pw_want > 1e-30)
+    assert np.abs(pw_got[small].astype(np.float64) - pw_want[small]).max(initial=0.0) <= 1e-29
+    if n_off:
+        off = ~same
+        cond = np.zeros(n_off)
+        ulp = 0.0
+        for r, lx, ly in lm:
+            prez = np.hypot(px_want[0, off].astype(np.float64) - lx, px_want[1, off].astype(np.float64) - ly)
+            cond += np.abs(prez - r) / sigma2
+            ulp = max(ulp, float(np.spacing(np.float32(prez.max()))))
+        tol = 1e-5 * np.abs(pw_want).max() + np.abs(pw_want[off]) * (cond * 4 * ulp + 32 * 2.0 ** -23)
+        assert (np.abs(pw_got[off].astype(np.float64) - pw_want[off]) <= tol).all()
 
 
 def test_pf_bitwise_when_trig_is_exact(engine):
@@ -162,10 +182,16 @@ def test_pf_philox_mode_matches_oracle(engine):
     engine.pf_predict_weight(pxd, pwd, None, lm, seed=0x1234_5678_9ABC)
     torch.cuda.synchronize()
     pxo, pwo = O.pf_predict_weight_batched(px, pw, None, lm, seed=0x1234_5678_9ABC)
-    # Box-Muller through logf/sinf/cosf of two libms: the noise itself differs by a few ulp
-    assert np.abs(pxd.cpu().numpy() - pxo).max() <= 2e-5 * max(1.0, np.abs(pxo).max())
+    # Box-Muller: sin/cos of the angle carry the host libm's bits, logf is CUDA's (<= 1 ulp from glibc's), so
+    # the noise and with it the predicted positions agree to an ulp or two: gated at 1e-5 on the POSITIONS.
+    # (The weights are exp(-dz^2 / 2 sigma^2) of those positions, 3e-5 per ulp and landmark: their gate with
+    # identical noise is test_pf_device_matches_oracle.)
+    got_x = pxd.cpu().numpy()
+    assert (np.abs(got_x - pxo).max(axis=1) <= 1e-5 * np.maximum(1.0, np.abs(pxo).max(axis=1))).all()
+    assert np.mean(got_x == pxo) > 0.9           # most coordinates are in fact identical
     got, want = pwd.cpu().numpy(), pwo
-    assert np.abs(np.log(np.maximum(got, 1e-37)) - np.log(np.maximum(want, 1e-37)))[want > 1e-30].max() < 0.05
+    lw = np.abs(np.log(np.maximum(got, 1e-37)) - np.log(np.maximum(want, 1e-37)))[want > 1e-30]
+    assert lw.max() < 0.02 and np.median(lw) < 1e-4
 
 
 def test_pf_host_entry_matches_device_entry_bitwise(engine):
@@ -551,6 +577,8 @@ def test_full_size_ekf_2pow20_matches_oracle_and_is_shard_invariant(engine):
     torch.cuda.synchronize()
     xo, Po = O.ekf_step_batched(x, P, z, u)
     assert field_err(xd.cpu().numpy(), xo) <= 1e-5 and field_err(Pd.cpu().numpy(), Po) <= 1e-5
+    same = (xd.cpu().numpy() == xo).all(axis=0) & (Pd.cpu().numpy() == Po).all(axis=0)
+    assert (~same).sum() <= 8, int((~same).sum())      # bit-identical but for glibc-FMA rounding cases (2e-8 / call)
     k = 524_289
     parts = []
     for sl in (slice(0, k), slice(k, n)):
@@ -573,8 +601,7 @@ def test_full_size_pf_2pow20_matches_oracle_and_is_shard_invariant(engine):
     engine.pf_predict_weight(pxd, pwd, nd, lm)
     torch.cuda.synchronize()
     pxo, pwo = O.pf_predict_weight_batched(px, pw, noise, lm)
-    assert np.abs(pxd.cpu().numpy() - pxo).max() <= 1e-5 * max(1.0, np.abs(pxo).max())
-    _assert_weights_close(pwd.cpu().numpy(), pwo, pxo, lm)
+    _assert_pf_parity(pxd.cpu().numpy(), pwd.cpu().numpy(), pxo, pwo, lm)   # per-particle 1e-5 on w at 2^20
     k = 1 << 19
     outs = []
     for sl in (slice(0, k), slice(k, n)):

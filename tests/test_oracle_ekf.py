@@ -142,3 +142,29 @@ def test_best_effort_build_is_a_timing_arm_that_stays_close():
     assert np.array_equal(xa, xc) and np.array_equal(Pa, Pc)
     err = lambda g, w: (np.abs(g - w).max(axis=0) / np.abs(w).max(axis=0)).max()  # noqa: E731
     assert err(xb, xa) <= 1e-5 and err(Pb, Pa) <= 1e-5
+
+
+def test_restated_glibc_sincosf_carries_this_hosts_libm_bits():
+    """The CUDA kernels evaluate sin/cos with glibc's binary64 algorithm (crb_sincosf_libm, crb_common.cuh); its C
+    restatement in the oracle is pinned here against the libm of THIS host over ~6e7 arguments in |y| < 120:
+    sin identical; cos identical except where glibc's ifunc-selected FMA build rounds an intermediate differently
+    (a few in 1e8)."""
+    import ctypes as C
+    from oracle import oracle as O
+    L = O.lib()
+    L.crb_oracle_libm_sincosf_census.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+    L.crb_oracle_libm_sincosf.argtypes = [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    out = np.zeros(2, np.int64)
+    L.crb_oracle_libm_sincosf_census(0, 0x42F00000, 37, out.ctypes.data)   # every 37th float in [0, 120), both signs
+    n = 2 * (0x42F00000 // 37)
+    assert out[0] <= 2e-7 * n and out[1] <= 2e-7 * n, out
+    # the workloads' range, densely: yaw in [-pi - 1, pi + 1]
+    lo = np.float32(0.5).view(np.uint32)
+    hi = np.float32(4.2).view(np.uint32)
+    L.crb_oracle_libm_sincosf_census(int(lo), int(hi), 1, out.ctypes.data)
+    assert out[0] <= 4 and out[1] <= 4, out
+    s, c = C.c_float(), C.c_float()
+    for y, ws, wc in [(0.0, 0.0, 1.0), (1e-5, 1e-5, 1.0), (np.inf, np.nan, np.nan)]:
+        L.crb_oracle_libm_sincosf(C.c_float(y), C.byref(s), C.byref(c))
+        assert (np.isnan(s.value) and np.isnan(ws)) or s.value == np.float32(ws)
+        assert (np.isnan(c.value) and np.isnan(wc)) or c.value == np.float32(wc)
