@@ -52,14 +52,14 @@ struct MpcTaskArgs {
 
 // Scheduling state of one CTA (shared memory, after the slots).  Everything except `seq` is read and
 // written under `lock` only.
-struct MpcSched {
+struct alignas(16) MpcSched {  // 16-byte multiple: the cp.async rings follow it
   int q[3][MPC_TASK_QS];  // slots waiting for a REFILL / BW / FW sweep (ring buffers)
   int head[3], tail[3];   // monotonic positions into q[k]
   int inflight;           // warps that are executing a task
   int lock;
   int seq;                // bumped whenever work is posted: idle warps watch it instead of the lock
-  int pad;
 };
+static_assert(sizeof(MpcSched) % 16 == 0, "record rings must start 16-byte aligned");
 
 __device__ __forceinline__ unsigned lanemask_lt() {
   unsigned m;
@@ -98,15 +98,16 @@ crb_mpc_tasks_kernel(const __grid_constant__ MpcTaskArgs A, const __grid_constan
   int slot = 0, next = MPC_PH_DEAD;
   for (;;) {
     // ---- one critical section per task: publish the finished sweep's slots, take the next batch -------
-    int got = 1;
-    if (lane == 0) {
-      int tries = 0;
-      while (atomicCAS(&sc->lock, 0, 1) != 0) {
-        __nanosleep(32);
-        if (++tries > (1 << 24)) { atomicExch(&A.header[1], 1ull); got = 0; break; }
-      }
+    // the whole warp polls together (lane 0 does the atomic, everybody sleeps): no divergent spin loop
+    int got = 0;
+    for (int tries = 0;; ++tries) {
+      int old = 1;
+      if (lane == 0) old = atomicCAS(&sc->lock, 0, 1);
+      old = __shfl_sync(FULL, old, 0);
+      if (old == 0) { got = 1; break; }
+      if (tries > (1 << 22)) { if (lane == 0) atomicExch(&A.header[1], 1ull); break; }
+      __nanosleep(tries < 4 ? 40 : 200);
     }
-    got = __shfl_sync(FULL, got, 0);
     if (!got) break;  // never hang the GPU on a scheduling bug: raise the error word and leave
     __threadfence_block();
     if (have_post) {
@@ -150,7 +151,7 @@ crb_mpc_tasks_kernel(const __grid_constant__ MpcTaskArgs A, const __grid_constan
       if (infl == 0) break;  // nothing waits and nobody is working: this CTA is done
       int spins = 0;         // wait for the next post without touching the lock
       while (*(volatile int*)&sc->seq == seen) {
-        __nanosleep(128);
+        __nanosleep(400);
         if (++spins > (1 << 23)) { if (lane == 0) atomicExch(&A.header[1], 2ull); break; }
       }
       if (spins > (1 << 23)) break;
