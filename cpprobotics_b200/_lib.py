@@ -66,6 +66,12 @@ PROTOTYPES = {
                                        C.c_void_p, C.POINTER(EkfParams), C.c_int]),
     "crb_ekf_step_batched_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.c_void_p, C.POINTER(EkfParams), C.c_int]),
+    "crb_ekf_track_open": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "crb_ekf_track_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(EkfParams),
+                                     C.c_void_p, C.c_int]),
+    "crb_ekf_track_sync": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "crb_ekf_track_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "crb_ekf_track_close": (C.c_int, [C.c_void_p, C.c_void_p]),
     "crb_pf_default_params": (None, [C.POINTER(PfParams)]),
     "crb_pf_predict_weight_batched": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                                 C.c_void_p, C.c_uint64, C.c_void_p, C.c_int,

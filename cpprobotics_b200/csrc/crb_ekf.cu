@@ -411,3 +411,123 @@ extern "C" int crb_ekf_step_batched_host(crb_ctx* ctx, int64_t n, float* x, floa
   for (int s = 0; s < CRB_N_PIPE; ++s) CRB_CUDA(cudaStreamSynchronize(ctx->pipe_stream[s]));
   return CRB_OK;
 }
+
+
+// ---- resident-state tracking: the reference's own time loop ----------------------------------------------
+// src/extended_kalman_filter.cpp:171-183 keeps xEst, PEst across iterations and receives only (z, u) per step.
+// crb_ekf_step_batched_host ships all 176 bytes per update every call, which pins the end-to-end rate to the
+// PCIe link (96 B in + 80 B out).  A track keeps x and P in HBM; a step ships 16 B in (z, u) and, if asked,
+// 16 B out (x).  Pinned + mapped z / u are read by the kernel straight over PCIe; x goes back through a
+// device-side snapshot on a second stream, so the D2H copy of step k overlaps the kernel of step k+1 (the two
+// directions of the link at once).
+struct crb_ekf_track {
+  int64_t n;
+  float* x;        // [4][n]
+  float* P;        // [16][n]
+  float* snap[2];  // [4][n] each: x of the last two steps on their way to the host
+  float* stage;    // [4][n]: z, u staging for pageable callers (allocated on first use)
+  cudaEvent_t ev_kernel[2], ev_copy[2];
+  int parity;
+  int64_t steps;
+};
+
+extern "C" int crb_ekf_track_open(crb_ctx* ctx, int64_t n, const float* x0_host, const float* P0_host,
+                                  crb_ekf_track** out) {
+  CRB_REQUIRE(ctx != nullptr && out != nullptr, "ctx / out is NULL");
+  CRB_REQUIRE(n > 0 && x0_host && P0_host, "n <= 0 or NULL initial state");
+  CRB_DEVICE_GUARD(ctx);
+  *out = nullptr;
+  crb_ekf_track* t = new crb_ekf_track();
+  memset(t, 0, sizeof(*t));
+  t->n = n;
+  const size_t row = (size_t)n * sizeof(float);
+  cudaError_t e = cudaMalloc(&t->x, 4 * row);
+  if (e == cudaSuccess) e = cudaMalloc(&t->P, 16 * row);
+  for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaMalloc(&t->snap[k], 4 * row);
+  for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&t->ev_kernel[k], cudaEventDisableTiming);
+  for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&t->ev_copy[k], cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaMemcpy(t->x, x0_host, 4 * row, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(t->P, P0_host, 16 * row, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    crb_set_error("crb_ekf_track_open: %s", cudaGetErrorString(e));
+    crb_ekf_track_close(ctx, t);
+    return e == cudaErrorMemoryAllocation ? CRB_ERR_ALLOC : CRB_ERR_CUDA;
+  }
+  *out = t;
+  return CRB_OK;
+}
+
+extern "C" int crb_ekf_track_close(crb_ctx* ctx, crb_ekf_track* t) {
+  CRB_REQUIRE(ctx != nullptr, "ctx is NULL");
+  if (!t) return CRB_OK;
+  CRB_DEVICE_GUARD(ctx);
+  cudaStreamSynchronize(ctx->pipe_stream[0]);
+  cudaStreamSynchronize(ctx->pipe_stream[1]);
+  if (t->x) cudaFree(t->x);
+  if (t->P) cudaFree(t->P);
+  for (int k = 0; k < 2; ++k) {
+    if (t->snap[k]) cudaFree(t->snap[k]);
+    if (t->ev_kernel[k]) cudaEventDestroy(t->ev_kernel[k]);
+    if (t->ev_copy[k]) cudaEventDestroy(t->ev_copy[k]);
+  }
+  if (t->stage) cudaFree(t->stage);
+  delete t;
+  return CRB_OK;
+}
+
+extern "C" int crb_ekf_track_sync(crb_ctx* ctx, crb_ekf_track* t) {
+  CRB_REQUIRE(ctx != nullptr && t != nullptr, "ctx / track is NULL");
+  CRB_DEVICE_GUARD(ctx);
+  CRB_CUDA(cudaStreamSynchronize(ctx->pipe_stream[0]));
+  CRB_CUDA(cudaStreamSynchronize(ctx->pipe_stream[1]));
+  return CRB_OK;
+}
+
+extern "C" int crb_ekf_track_step(crb_ctx* ctx, crb_ekf_track* t, const float* z_host, const float* u_host,
+                                  const crb_ekf_params* prm, float* x_out_host, int async) {
+  CRB_REQUIRE(ctx != nullptr && t != nullptr && prm != nullptr, "ctx / track / prm is NULL");
+  CRB_REQUIRE(z_host && u_host, "NULL observation / control array");
+  CRB_DEVICE_GUARD(ctx);
+  const int64_t n = t->n;
+  const size_t row = (size_t)n * sizeof(float);
+  cudaStream_t sk = ctx->pipe_stream[0], sc = ctx->pipe_stream[1];
+  const int p = t->parity;
+  const float *mz = nullptr, *mu = nullptr;
+  const bool direct = crb_zero_copy_enabled() && crb_host_mapped(z_host, &mz) && crb_host_mapped(u_host, &mu);
+  if (!direct) {  // pageable (or zero-copy disabled): stage z, u through the device
+    if (!t->stage) CRB_CUDA(cudaMalloc(&t->stage, 4 * row));
+    CRB_CUDA(cudaMemcpyAsync(t->stage, z_host, 2 * row, cudaMemcpyHostToDevice, sk));
+    CRB_CUDA(cudaMemcpyAsync(t->stage + 2 * n, u_host, 2 * row, cudaMemcpyHostToDevice, sk));
+    mz = t->stage;
+    mu = t->stage + 2 * n;
+  }
+  int rc = ekf_launch(ctx, sk, n, n, t->x, t->P, mz, mu, n, 1, prm);
+  if (rc) return rc;
+  if (x_out_host) {
+    // snapshot p was last used two steps ago: its copy must have left before it is overwritten
+    if (t->steps >= 2) CRB_CUDA(cudaStreamWaitEvent(sk, t->ev_copy[p], 0));
+    CRB_CUDA(cudaMemcpyAsync(t->snap[p], t->x, 4 * row, cudaMemcpyDeviceToDevice, sk));
+    CRB_CUDA(cudaEventRecord(t->ev_kernel[p], sk));
+    CRB_CUDA(cudaStreamWaitEvent(sc, t->ev_kernel[p], 0));
+    CRB_CUDA(cudaMemcpyAsync(x_out_host, t->snap[p], 4 * row, cudaMemcpyDeviceToHost, sc));
+    CRB_CUDA(cudaEventRecord(t->ev_copy[p], sc));
+    t->parity ^= 1;
+    t->steps++;
+  }
+  if (!async) {
+    CRB_CUDA(cudaStreamSynchronize(sk));
+    CRB_CUDA(cudaStreamSynchronize(sc));
+  }
+  return CRB_OK;
+}
+
+extern "C" int crb_ekf_track_read(crb_ctx* ctx, crb_ekf_track* t, float* x_host, float* P_host) {
+  CRB_REQUIRE(ctx != nullptr && t != nullptr, "ctx / track is NULL");
+  CRB_DEVICE_GUARD(ctx);
+  const size_t row = (size_t)t->n * sizeof(float);
+  CRB_CUDA(cudaStreamSynchronize(ctx->pipe_stream[0]));
+  CRB_CUDA(cudaStreamSynchronize(ctx->pipe_stream[1]));
+  if (x_host) CRB_CUDA(cudaMemcpy(x_host, t->x, 4 * row, cudaMemcpyDeviceToHost));
+  if (P_host) CRB_CUDA(cudaMemcpy(P_host, t->P, 16 * row, cudaMemcpyDeviceToHost));
+  return CRB_OK;
+}

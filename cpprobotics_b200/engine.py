@@ -136,6 +136,33 @@ class Engine:
         self._ekf(self.lib.crb_ekf_step_batched_host, False, x, P, z, u, params, n_steps)
 
     # ---- PF ---------------------------------------------------------------------------------------
+    # resident-state tracking: the reference's time loop (:171-183), 16 B in / 16 B out per update
+    def ekf_track_open(self, x0, P0):
+        n = int(x0.shape[-1])
+        _shape(x0, 4, n, "x0"); _shape(P0, 16, n, "P0")
+        h = C.c_void_p()
+        check(self.lib.crb_ekf_track_open(self.ctx, n, _ptr(x0, np.float32, device=False, name="x0"),
+                                          _ptr(P0, np.float32, device=False, name="P0"), C.byref(h)),
+              "crb_ekf_track_open")
+        return h
+
+    def ekf_track_step(self, trk, z, u, params: Optional[EkfParams] = None, x_out=None, async_: bool = False):
+        prm = params if params is not None else ekf_default_params()
+        check(self.lib.crb_ekf_track_step(self.ctx, trk, _ptr(z, np.float32, device=False, name="z"),
+                                          _ptr(u, np.float32, device=False, name="u"), C.byref(prm),
+                                          _ptr(x_out, np.float32, device=False, name="x_out"), int(bool(async_))),
+              "crb_ekf_track_step")
+
+    def ekf_track_sync(self, trk):
+        check(self.lib.crb_ekf_track_sync(self.ctx, trk), "crb_ekf_track_sync")
+
+    def ekf_track_read(self, trk, x=None, P=None):
+        check(self.lib.crb_ekf_track_read(self.ctx, trk, _ptr(x, np.float32, device=False, name="x"),
+                                          _ptr(P, np.float32, device=False, name="P")), "crb_ekf_track_read")
+
+    def ekf_track_close(self, trk):
+        check(self.lib.crb_ekf_track_close(self.ctx, trk), "crb_ekf_track_close")
+
     def _pf(self, fn, dev, px, pw, noise, landmarks, params, seed):
         n = int(px.shape[-1])
         _shape(px, 4, n, "px"); _shape(pw, 1, n, "pw")

@@ -115,6 +115,26 @@ int crb_ekf_step_batched(crb_ctx* ctx, int64_t n, float* x, float* P, const floa
 int crb_ekf_step_batched_host(crb_ctx* ctx, int64_t n, float* x, float* P, const float* z,
                               const float* u, const crb_ekf_params* prm, int n_steps);
 
+/* Resident-state tracking: the reference's own time loop (src/extended_kalman_filter.cpp:171-183 keeps
+ * xEst, PEst across iterations and receives only z, u per step).  A track owns x [4][n] and P [16][n] in device
+ * memory; crb_ekf_track_step runs ONE filter step for all n agents from HOST arrays z [2][n], u [2][n] (16 bytes
+ * per update over PCIe instead of the 176 of crb_ekf_step_batched_host; pinned + mapped arrays are read by the
+ * kernel in place) and, when x_out_host != NULL, returns x [4][n] to the host (16 bytes per update, copied on a
+ * second stream so that it overlaps the next step's kernel).
+ *   async = 0: returns when x_out_host is complete.
+ *   async = 1: returns after enqueueing; z_host / u_host / x_out_host of this step belong to the library until
+ *              crb_ekf_track_sync (or a later synchronous step) returns.  At most two steps' outputs are in
+ *              flight; rotate two sets of host buffers.
+ * crb_ekf_track_read copies the current x and / or P to the host (synchronises first).  Results are bit-identical
+ * to crb_ekf_step_batched with the same inputs. */
+typedef struct crb_ekf_track crb_ekf_track;
+int crb_ekf_track_open(crb_ctx* ctx, int64_t n, const float* x0_host, const float* P0_host, crb_ekf_track** out);
+int crb_ekf_track_step(crb_ctx* ctx, crb_ekf_track* trk, const float* z_host, const float* u_host,
+                       const crb_ekf_params* prm, float* x_out_host, int async);
+int crb_ekf_track_sync(crb_ctx* ctx, crb_ekf_track* trk);
+int crb_ekf_track_read(crb_ctx* ctx, crb_ekf_track* trk, float* x_host, float* P_host);
+int crb_ekf_track_close(crb_ctx* ctx, crb_ekf_track* trk);
+
 /* ---- particle filter -------------------------------------------------------------------------- */
 /* Constants from src/particle_filter.cpp: DT :18, PI :19 (3.141592653, *not* M_PI), Q :217 (0.01),
  * Rsim :228-230.  rsim_diag are the two diagonal entries Rsim(0,0), Rsim(1,1) used at :87-88. */

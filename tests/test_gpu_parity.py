@@ -704,3 +704,40 @@ def test_cuda_path_against_reference_text_outputs(engine):
     engine.mpc_plant_update(sd, u0d)
     torch.cuda.synchronize()
     assert np.abs(sd.cpu().numpy() - G["upd_out"]).max() <= 1e-5 * np.abs(G["upd_out"]).max()
+
+
+# ---- resident-state EKF tracking (the reference's time loop, :171-183) -------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("pinned", [True, False])
+def test_ekf_track_matches_the_multi_step_launch_bitwise(engine, pinned):
+    """K single steps through crb_ekf_track_step (x, P resident on the device, 16 B in / 16 B out per update)
+    must give the bits of ONE launch with n_steps = K on the same observations, synchronous and pipelined."""
+    import torch
+    n, K = 70_001, 6
+    x, P, z, u = synth.ekf_inputs(n, n_steps=K)
+    xd, Pd, zd, ud = _dev(x, P, z, u)
+    engine.ekf_estimation(xd, Pd, zd, ud, n_steps=K)
+    torch.cuda.synchronize()
+    want_x, want_P = xd.cpu().numpy(), Pd.cpu().numpy()
+
+    def host(a):
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        return t.pin_memory() if pinned else t
+    for async_ in (False, True):
+        trk = engine.ekf_track_open(x, P)
+        zs = [host(z[2 * k:2 * k + 2]) for k in range(K)]
+        us = [host(u[2 * k:2 * k + 2]) for k in range(K)]
+        outs = [host(np.zeros((4, n), np.float32)) for _ in range(K)]
+        for k in range(K):
+            engine.ekf_track_step(trk, zs[k], us[k], x_out=outs[k], async_=async_)
+        engine.ekf_track_sync(trk)
+        gx, gP = np.empty_like(x), np.empty_like(P)
+        engine.ekf_track_read(trk, gx, gP)
+        engine.ekf_track_close(trk)
+        assert np.array_equal(gx, want_x) and np.array_equal(gP, want_P)
+        assert np.array_equal(outs[-1].numpy(), want_x)
+        # every intermediate x is what a (k+1)-step launch gives
+        xk, Pk = _dev(x, P)
+        engine.ekf_estimation(xk, Pk, _dev(z[:6])[0], _dev(u[:6])[0], n_steps=3)
+        torch.cuda.synchronize()
+        assert np.array_equal(outs[2].numpy(), xk.cpu().numpy())
