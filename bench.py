@@ -9,14 +9,20 @@ A "step" is one pass of the hot path over one batch of synthetic input (BASELINE
   ekf (headline, configs[1]): 2^20 agents x 1 EKF update per GPU          metric: EKF updates/s
   pf  (configs[2]):           2^20 particles x 8 landmarks per GPU        metric: particle updates/s
   mpc (configs[3]/[4]):       65 536 agents, T=20 per GPU                 metric: MPC solves/s
-The default run prints ONE JSON line whose headline is the EKF config; the PF and MPC configs are
-measured in the same run and reported under "extra" with their own roofline / cpu_baseline / e2e.
-Weak scaling: per-GPU work is fixed, shard r holds global indices [r*n, (r+1)*n) of the
-index-addressed generators; the only inter-GPU traffic is one all-gather of 8 doubles per rank.
+The default run prints ONE JSON line whose headline is the EKF config.  BASELINE.json's metric is "EKF updates/sec
+& MPC solves/sec", so the MPC (and PF) figures of the same run are FIRST-CLASS in that line: `roofline.mpc`,
+`e2e.mpc`, `cpu_baseline.mpc` (same for `pf`), `config.mpc_solves_per_s`, and with --gpus N > 1 BASELINE
+configs[4] as written (`config5`: 2^20 MPC agents sharded over the N GPUs, one stats all-gather per call).  The
+full per-workload records stay under "extra".
+Weak scaling (headline): per-GPU work is fixed, shard r holds global indices [r*n, (r+1)*n) of the
+index-addressed generators; the only inter-GPU traffic is one all-gather of 8 doubles per rank, issued by
+libcrb's own NCCL communicator (crb_gather_stats) INSIDE the captured graph.
 
 Timing rules followed: W >= 3 warm-up steps; inputs rotate over 3 buffer sets whose total exceeds the
-126 MB L2; device time from CUDA events on the launching stream, bracketed by barrier + synchronize,
-max over ranks; SM clocks sampled with nvidia-smi during the timed region.
+126 MB L2; the K steps (+ stats tail + all-gather) are captured once and replayed >= 10 times, every replay
+timed with CUDA events on the launching stream, the whole series bracketed by barrier + synchronize, each replay's
+time maxed over ranks; `ms_per_step` is the MEDIAN replay / K and the minimum is reported beside it; SM clocks
+sampled with nvidia-smi during the timed region.
 
 `--impl reference` times the CPU restatement of the reference (oracle/, the only implementation of the
 path that can run here: Eigen/IPOPT are absent) on the box's host cores with all threads.
@@ -48,9 +54,16 @@ MPC_BYTES = 344 + 472 # read x0 4 + xref 80, write sol 118 + u0 2 (+cost,status,
 NSETS = 3
 
 
+PINNED_CPUS = [0]
+
+
 def host_threads() -> int:
     """All host cores this process may use.  torchrun exports OMP_NUM_THREADS=1, which would silently make the
-    CPU arm single-threaded; the oracle takes an explicit thread count instead."""
+    CPU arm single-threaded; the oracle takes an explicit thread count instead.  Once the CPU arm has pinned the
+    process (cpu_pin_one_numa_node) the count is the size of THAT set: with OMP_PROC_BIND the OpenMP runtime binds
+    the calling thread to a single core, so the affinity mask read later would say 1."""
+    if PINNED_CPUS[0]:
+        return PINNED_CPUS[0]
     try:
         return max(1, len(os.sched_getaffinity(0)))
     except AttributeError:
@@ -171,9 +184,13 @@ def max_over_ranks_cpu(ms: float, world: int) -> float:
     return float(t.item())
 
 
-def gather_stats(stats, world):
-    """The single collective of the data path: all-gather of CRB_STATS_LEN doubles per rank."""
+def gather_stats(stats, world, eng=None, out=None):
+    """The single collective of the data path: all-gather of CRB_STATS_LEN doubles per rank.  On the GPU it is
+    libcrb's own NCCL communicator (crb_gather_stats, capturable in a CUDA graph); the torch.distributed form
+    is what the CPU (gloo) tests of the host logic use."""
     import torch
+    if eng is not None and (world == 1 or eng.world == world):
+        return eng.gather_stats(stats, out=out)
     if world == 1:
         return stats.unsqueeze(0)
     import torch.distributed as dist
@@ -182,21 +199,77 @@ def gather_stats(stats, world):
     return out.view(world, stats.numel())
 
 
+def comm_setup(eng, rank, world):
+    """Bootstrap libcrb's communicator: rank 0 creates the NCCL unique id, torch.distributed (already up for the
+    barrier / max-over-ranks plumbing) carries the 128 bytes."""
+    if world == 1:
+        return
+    import torch
+    import torch.distributed as dist
+    from cpprobotics_b200 import _lib as L
+    buf = torch.zeros(L.CRB_COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        buf.copy_(torch.frombuffer(bytearray(eng.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(buf, 0)
+    eng.comm_init(world, rank, bytes(buf.cpu().numpy().tobytes()))
+
+
+def numa_pinned(a, device_index=0):
+    """Pinned host copy of `a` allocated while this thread runs on the CPUs of the GPU's NUMA node, so that the
+    pages are first-touched there (eight GPUs pulling from one node's DRAM was r1's e2e limiter at N = 8)."""
+    import torch
+    old = None
+    try:
+        node = None
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id if hasattr(
+            torch.cuda.get_device_properties(device_index), "pci_bus_id") else None
+        if bus is not None:
+            dom = torch.cuda.get_device_properties(device_index).pci_domain_id
+            devid = torch.cuda.get_device_properties(device_index).pci_device_id
+            path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{devid:02x}.0/numa_node"
+            if os.path.exists(path):
+                node = int(open(path).read().strip())
+        if node is not None and node >= 0:
+            cl = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
+            cpus = set()
+            for part in cl.split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+            old = os.sched_getaffinity(0)
+            use = cpus & old
+            if use:
+                os.sched_setaffinity(0, use)
+    except Exception:
+        old = None
+    try:
+        t = torch.empty(a.shape, dtype=torch.from_numpy(a).dtype).pin_memory()
+        t.copy_(torch.from_numpy(a))
+    finally:
+        if old is not None:
+            os.sched_setaffinity(0, old)
+    return t
+
+
 def pinned(a):
     import torch
-    t = torch.from_numpy(a).pin_memory()
-    return t
+    return numa_pinned(np.ascontiguousarray(a), torch.cuda.current_device())
 
 
 # =========================================================================================================
 # workloads: each returns a dict with value / ms_per_step / roofline / e2e / cpu_baseline pieces
 # =========================================================================================================
-def time_device_steps(step_fn, steps, warmup, world, after_fn=None, eng=None, graph=True):
-    """W untimed + K timed steps between barrier+sync brackets; CUDA events on the launching stream.
-    The K steps (+ the optional tail) are captured once into a CUDA graph and the timed region is one
-    replay of it, so that host-side launch overhead (Python/ctypes) is not what is measured; if capture
-    is not possible the steps are enqueued directly.  Returns (ms, mode)."""
+REPLAYS = 10
+LAST_TIMING = {}
+
+
+def time_device_steps(step_fn, steps, warmup, world, after_fn=None, eng=None, graph=True, reps=None):
+    """W untimed steps, then the K steps (+ the optional tail: stats reduction and the all-gather) captured ONCE
+    into a CUDA graph and replayed `reps` (>= 10) times.  Every replay is timed with its own pair of CUDA events
+    on the launching stream; the series is bracketed by barrier + synchronize on both sides and each replay's time
+    is maxed over ranks.  Returns (median replay ms, mode); LAST_TIMING holds min / median / all replays.  If
+    capture is not possible the K steps are enqueued directly, also `reps` times."""
     import torch
+    reps = REPLAYS if reps is None else reps
     for k in range(warmup):
         step_fn(k)
     if after_fn is not None:
@@ -211,7 +284,7 @@ def time_device_steps(step_fn, steps, warmup, world, after_fn=None, eng=None, gr
                 eng.bind_current_stream()
                 for k in range(steps):
                     step_fn(warmup + k)
-                if after_fn is not None and world == 1:
+                if after_fn is not None:
                     after_fn()
             eng.bind_current_stream()
             g.replay()                      # one untimed replay
@@ -221,20 +294,36 @@ def time_device_steps(step_fn, steps, warmup, world, after_fn=None, eng=None, gr
             eng.bind_current_stream()
             g = None
     barrier_sync(world)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    if g is not None:
-        g.replay()
-        if after_fn is not None and world > 1:
-            after_fn()                      # the NCCL all-gather stays outside the graph
-    else:
-        for k in range(steps):
-            step_fn(warmup + k)
-        if after_fn is not None:
-            after_fn()
-    e1.record()
+    evs = []
+    for r in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        if g is not None:
+            g.replay()
+        else:
+            for k in range(steps):
+                step_fn(warmup + k)
+            if after_fn is not None:
+                after_fn()
+        e1.record()
+        evs.append((e0, e1))
     barrier_sync(world)
-    return max_over_ranks(e0.elapsed_time(e1), world), mode
+    ms = torch.tensor([a.elapsed_time(b) for a, b in evs], dtype=torch.float64, device="cuda")
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    v = ms.cpu().numpy()
+    LAST_TIMING.clear()
+    LAST_TIMING.update(replays=int(reps), steps_per_replay=int(steps), ms_median=float(np.median(v)),
+                       ms_min=float(v.min()), ms_max=float(v.max()), mode=mode)
+    return float(np.median(v)), mode
+
+
+def timing_record(steps):
+    t = dict(LAST_TIMING)
+    return dict(replays=t.get("replays"), steps_per_replay=t.get("steps_per_replay"),
+                ms_per_step_median=t.get("ms_median", 0.0) / steps, ms_per_step_min=t.get("ms_min", 0.0) / steps,
+                ms_per_step_max=t.get("ms_max", 0.0) / steps, launch=t.get("mode"))
 
 
 def time_host_steps(step_fn, steps, warmup, world):
@@ -251,28 +340,70 @@ def time_host_steps(step_fn, steps, warmup, world):
     return max_over_ranks(ms, world)
 
 
-def cpu_time(fn, units_per_call, budget_s=6.0, min_calls=2):
-    """Bounded CPU sample: repeat fn until ~budget_s of wall time; returns units/s."""
+def cpu_pin_one_numa_node():
+    """CPU arm hygiene (r1's CPU figures swung 6x between boxes): restrict this process to the CPUs of ONE NUMA
+    node (the one with the most CPUs in our affinity mask) before the OpenMP runtime starts, and ask it to bind
+    threads to cores.  Returns (restore_fn, description)."""
+    old = os.sched_getaffinity(0)
+    best, best_node = set(), None
+    try:
+        for d in sorted(os.listdir("/sys/devices/system/node")):
+            if not d.startswith("node") or not d[4:].isdigit():
+                continue
+            cpus = set()
+            for part in open(f"/sys/devices/system/node/{d}/cpulist").read().strip().split(","):
+                if not part:
+                    continue
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+            use = cpus & old
+            if len(use) > len(best):
+                best, best_node = use, d
+    except OSError:
+        pass
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "cores")
+
+    def restore():
+        PINNED_CPUS[0] = 0
+        os.sched_setaffinity(0, old)
+    if best and len(best) < len(old):
+        os.sched_setaffinity(0, best)
+        PINNED_CPUS[0] = len(best)
+        return restore, f"{len(best)} CPUs of NUMA {best_node} (of {len(old)} allowed)"
+    PINNED_CPUS[0] = len(old)
+    return restore, f"{len(old)} allowed CPUs (single NUMA node or no topology information)"
+
+
+def cpu_time(fn, units_per_call, budget_s=6.0, min_passes=5):
+    """Bounded CPU sample: >= 5 timed passes (more until ~budget_s), each timed on its own; returns the MEDIAN
+    rate in units/s plus the spread, so that one descheduled pass does not move the figure."""
     fn()  # warm caches / thread pool
-    t0 = time.perf_counter()
-    calls = 0
+    ts = []
+    t_all = time.perf_counter()
     while True:
+        t0 = time.perf_counter()
         fn()
-        calls += 1
-        el = time.perf_counter() - t0
-        if calls >= min_calls and el >= budget_s:
+        ts.append(time.perf_counter() - t0)
+        el = time.perf_counter() - t_all
+        if len(ts) >= min_passes and el >= budget_s:
             break
-        if el > 4 * budget_s:
+        if el > 4 * budget_s and len(ts) >= 2:
             break
-    return units_per_call * calls / el, calls, el
+    ts = np.array(ts)
+    spread = dict(passes=int(ts.size), fastest=units_per_call / ts.min(), slowest=units_per_call / ts.max())
+    CPU_SPREAD.append(spread)
+    return units_per_call / float(np.median(ts)), int(ts.size), float(ts.sum())
+
+
+CPU_SPREAD = []
 
 
 def tuned_threads(fn_thr, label=""):
-    """Thread count for a CPU arm.  "All the cores in the affinity mask" is not always the fastest choice:
-    on the B200 boxes (128 logical CPUs, other tenants running) 128 OpenMP threads measured 10x SLOWER than
-    64 (10.9 M vs 112.9 M EKF updates/s, scripts/zerocopy_probe.py), so the CPU arm times one call at
-    cores, 3/4, 1/2 and 1/4 of the mask and keeps the fastest -- the baseline is the best the host can
-    do, not a strawman."""
+    """Thread count for a CPU arm.  "All the cores in the affinity mask" is not always the fastest choice on
+    shared hosts (r1: 128 OpenMP threads measured 10x SLOWER than 64), so the arm times cores, 3/4, 1/2 and 1/4
+    of the mask, FIVE passes each, and keeps the team with the best median -- the baseline is the best the host
+    can do, not a strawman, and not a two-sample accident."""
     cores = host_threads()
     cand = sorted({max(1, cores), max(1, 3 * cores // 4), max(1, cores // 2), max(1, cores // 4)},
                   reverse=True)
@@ -280,11 +411,11 @@ def tuned_threads(fn_thr, label=""):
     for c in cand:
         fn_thr(c)                       # warm this team size
         ts = []
-        for _ in range(2):
+        for _ in range(5):
             t0 = time.perf_counter()
             fn_thr(c)
             ts.append(time.perf_counter() - t0)
-        t = min(ts)
+        t = float(np.median(ts))
         if best_t is None or t < best_t:
             best, best_t = c, t
     return best, cores
@@ -298,7 +429,21 @@ def best_effort(fn, units, budget_s=2.0):
         O.use_library("faithful")
         return None
     try:
-        v, _, _ = cpu_time(fn, units, budget_s=budget_s)
+        v, _, _ = cpu_time(fn, units, budget_s=budget_s, min_passes=3)
+    finally:
+        O.use_library("faithful")
+    return v
+
+
+def as_shipped_O0(fn, units, budget_s=1.0):
+    """the reference builds without optimisation (CMakeLists.txt:5): the same restatement at -O0,
+    recorded once for context."""
+    from oracle import oracle as O
+    if not O.use_library("O0"):
+        O.use_library("faithful")
+        return None
+    try:
+        v, _, _ = cpu_time(fn, units, budget_s=budget_s, min_passes=2)
     finally:
         O.use_library("faithful")
     return v
@@ -314,7 +459,7 @@ def bench_ekf(eng, rank, world, steps, warmup, with_cpu):
     for s in range(NSETS):   # identical contents, distinct memory: only residency matters
         sets.append(tuple(torch.from_numpy(a).to(dev) for a in host))
     stats = torch.zeros(8, dtype=torch.float64, device=dev)
-    l0 = eng.launches
+    table = torch.zeros((world, 8), dtype=torch.float64, device=dev)
 
     def step(k):
         x, P, z, u = sets[k % NSETS]
@@ -322,33 +467,63 @@ def bench_ekf(eng, rank, world, steps, warmup, with_cpu):
 
     def after():
         eng.stats_reduce(sets[0][0][0], i0=rank * n, out=stats)   # summary of the x field
-        gather_stats(stats, world)
+        gather_stats(stats, world, eng, out=table)                # libcrb's NCCL all-gather, inside the graph
 
-    l0 = eng.launches
     ms, mode = time_device_steps(step, steps, warmup, world, after, eng=eng)
-    launches = steps + 2                     # K filter kernels + the two stats-reduction kernels
+    timing = timing_record(steps)
+    launches = steps + 2 + (1 if world > 1 else 0)   # K filter kernels + two stats-reduction kernels (+ NCCL's)
     value = world * n * steps / (ms * 1e-3)
-    # roofline of the dominant kernel (one launch per step): algorithmic bytes / avg launch duration.
+    # roofline of the dominant kernel (one launch per step): algorithmic bytes / avg launch duration,
     # measured separately WITHOUT the stats tail so that it is the kernel alone.
     ms_k, _ = time_device_steps(step, steps, 3, world, eng=eng)
+    k_timing = timing_record(steps)
     peak, peak_src, _ = peaks()
     achieved = EKF_BYTES * n * steps / (ms_k * 1e-3) / 1e9
     copy_gbs = copy_ceiling_gbs()
-    # e2e through the host-pointer C-ABI entry: pinned host buffers, H2D + kernel + D2H every step
+    # e2e (a): one-shot through the host-pointer C-ABI entry: pinned host buffers, all 176 B per update cross
+    # PCIe every step
     hx, hP, hz, hu = (pinned(a) for a in host)
-    ms_e = time_host_steps(lambda k: eng.ekf_estimation_host(hx, hP, hz, hu), max(3, min(steps, 10)),
-                           warmup, world)
     e_steps = max(3, min(steps, 10))
-    out = dict(value=value, ms=ms / steps, launches=launches, launch_mode=mode,
+    ms_e = time_host_steps(lambda k: eng.ekf_estimation_host(hx, hP, hz, hu), e_steps, warmup, world)
+    # e2e (b): the reference's own loop shape (:171-183): x, P stay on the device, each step ships z, u (16 B)
+    # in and x (16 B) out, pipelined over two sets of pinned buffers
+    trk = eng.ekf_track_open(host[0], host[1])
+    zs = [pinned(host[2]) for _ in range(2)]
+    us = [pinned(host[3]) for _ in range(2)]
+    xo = [pinned(np.zeros((4, n), np.float32)) for _ in range(2)]
+    s_steps = max(10, steps)
+
+    def track(k):
+        eng.ekf_track_step(trk, zs[k & 1], us[k & 1], x_out=xo[k & 1], async_=True)
+    for k in range(4):
+        track(k)
+    eng.ekf_track_sync(trk)
+    barrier_sync(world)
+    t0 = time.perf_counter()
+    for k in range(s_steps):
+        track(k)
+    eng.ekf_track_sync(trk)
+    ms_s = max_over_ranks((time.perf_counter() - t0) * 1e3, world)
+    barrier_sync(world)
+    eng.ekf_track_close(trk)
+    out = dict(value=value, ms=ms / steps, launches=launches, launch_mode=mode, timing=timing,
                roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s",
                              frac=achieved / peak, traffic=traffic_for("ekf"), peak_source=peak_src,
                              kernel="crb_ekf_step_kernel",
                              algorithmic_bytes_per_launch=EKF_BYTES * n,
+                             ms_per_launch_median=k_timing["ms_per_step_median"],
+                             ms_per_launch_min=k_timing["ms_per_step_min"],
                              copy_gbs_same_run=copy_gbs, frac_of_copy_same_run=achieved / copy_gbs),
                e2e=dict(value=world * n * e_steps / (ms_e * 1e-3), unit="updates/s",
                         h2d_bytes_per_step=96 * n, d2h_bytes_per_step=80 * n,
-                        path="crb_ekf_step_batched_host on pinned buffers: kernel reads/writes host memory "
-                             "over PCIe directly (zero-copy), synchronous per step"))
+                        path="crb_ekf_step_batched_host on pinned buffers (NUMA-local to the GPU): kernel reads/"
+                             "writes host memory over PCIe directly (zero-copy), synchronous per step",
+                        resident_state=dict(
+                            value=world * n * s_steps / (ms_s * 1e-3), unit="updates/s",
+                            h2d_bytes_per_step=16 * n, d2h_bytes_per_step=16 * n, steps=s_steps,
+                            path="crb_ekf_track_step: x, P resident in HBM across steps (the reference's loop, "
+                                 ":171-183), z,u read over PCIe by the kernel, x returned through a snapshot copy "
+                                 "overlapped with the next step")))
     if with_cpu and rank == 0:
         out["cpu_baseline"] = cpu_ekf(host)
     return out
@@ -360,16 +535,22 @@ def cpu_ekf(host=None):
     n = EKF_N
     x, P, z, u = host if host is not None else synth.ekf_inputs(n)
     x, P = x.copy(), P.copy()
+    CPU_SPREAD.clear()
     thr, mask = tuned_threads(lambda c: O.ekf_step_batched(x, P, z, u, nthreads=c, inplace=True))
     v, calls, el = cpu_time(lambda: O.ekf_step_batched(x, P, z, u, nthreads=thr, inplace=True), n,
                             budget_s=5.0)
+    spread = CPU_SPREAD[-1]
     m = 1 << 18                                   # SURVEY d-7: the same code on ONE core
     x1, P1, z1, u1 = (np.ascontiguousarray(a[:, :m]) for a in (x, P, z, u))
-    v1, _, _ = cpu_time(lambda: O.ekf_step_batched(x1, P1, z1, u1, nthreads=1, inplace=True), m, budget_s=1.0)
+    v1, _, _ = cpu_time(lambda: O.ekf_step_batched(x1, P1, z1, u1, nthreads=1, inplace=True), m, budget_s=1.0,
+                        min_passes=3)
     vb = best_effort(lambda: O.ekf_step_batched(x, P, z, u, nthreads=thr, inplace=True), n)
+    v0 = as_shipped_O0(lambda: O.ekf_step_batched(x1, P1, z1, u1, nthreads=1, inplace=True), m)
     return dict(value=v, unit="updates/s", cores=thr, kind="port", single_core_value=v1, best_effort_value=vb,
-                sample=f"{calls} x {n} agents x 1 step, oracle/crb_oracle.c -O2 -ffp-contract=off, "
-                       f"OpenMP {thr} threads (fastest of 1/4..1 x the {mask}-cpu mask), {el:.1f} s")
+                b0_O0_single_core_value=v0, spread=spread,
+                sample=f"median of {calls} passes x {n} agents x 1 step, oracle/crb_oracle.c -O2 -ffp-contract=off, "
+                       f"OpenMP {thr} threads bound to cores (best median of 5 passes at 1/4..1 x the {mask}-cpu "
+                       f"mask), {el:.1f} s")
 
 
 def bench_pf(eng, rank, world, steps, warmup, with_cpu):
@@ -399,7 +580,7 @@ def bench_pf(eng, rank, world, steps, warmup, with_cpu):
     ms_e = time_host_steps(lambda k: eng.pf_predict_weight_host(hpx, hpw, hno, lm), e_steps, warmup,
                            world)
     out = dict(metric="PF particle updates/sec (predict+weight, 8 landmarks)", value=value,
-               unit="particles/s", ms_per_step=ms_k / steps,
+               unit="particles/s", ms_per_step=ms_k / steps, timing=timing_record(steps),
                config=dict(workload="pf_predict_weight_2^20_particles_8_landmarks_per_gpu",
                            l2=f"{len(sets)} rotating buffer sets, {len(sets) * 29} MB > 126 MB L2"),
                roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s",
@@ -475,7 +656,26 @@ def mpc_flops(iters_sum, n, T):
     return iters_sum * (T - 1) * (470.0 + 1.2 * 150.0)
 
 
-def bench_mpc(eng, rank, world, steps, warmup, with_cpu, n=None):
+FP32_PEAK = {}
+
+
+def fp32_peak(eng):
+    """Non-tensor fp32 FMA rate MEASURED in this run on this GPU (crb_probe_fp32_peak); nominal as fallback."""
+    if "v" not in FP32_PEAK:
+        sm_max = float(peaks()[2].get("sm_max_mhz", 1965.0))
+        nominal = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+        try:
+            v = eng.probe_fp32_peak()
+            FP32_PEAK.update(v=v, src=f"measured in this run: crb_probe_fp32_peak (register-only FFMA kernel, best of 5); "
+                                      f"nominal 148 SM x 128 lanes x 2 x {sm_max:.0f} MHz = {nominal:.1f}")
+        except Exception as exc:   # pragma: no cover
+            FP32_PEAK.update(v=nominal, src=f"nominal (probe failed: {exc})")
+    return FP32_PEAK["v"], FP32_PEAK["src"]
+
+
+def bench_mpc(eng, rank, world, steps, warmup, with_cpu, n=None, label=None, with_e2e=True):
+    """One step = one crb_mpc_solve_batched over this rank's n agents + the per-shard cost statistics + ONE
+    all-gather of them (BASELINE configs[3] / [4]; caller loop src/model_predictive_control.cpp:372-378)."""
     import torch
     from cpprobotics_b200 import mpc_default_params, synth
     n, T = (MPC_N if n is None else n), MPC_T
@@ -493,63 +693,119 @@ def bench_mpc(eng, rank, world, steps, warmup, with_cpu, n=None):
     status = torch.empty(n, dtype=torch.int32, device=dev)
     iters = torch.empty(n, dtype=torch.int32, device=dev)
     stats = torch.zeros(8, dtype=torch.float64, device=dev)
-    gathered = {}
+    table = torch.zeros((world, 8), dtype=torch.float64, device=dev)
 
     def step(k):
         s, xr = sets[k % NSETS]
         eng.mpc_solve(s, xr, T, prm, sol=sol, u0=u0, cost=cost, status=status, iters=iters)
         eng.stats_reduce(cost, status, iters, i0=rank * n, out=stats)
-        gathered["g"] = gather_stats(stats, world)   # config 5: NCCL gather of cost stats per call
+        gather_stats(stats, world, eng, out=table)     # config 5: the gather of cost stats, every call
 
     def step_kernel_only(k):
         s, xr = sets[k % NSETS]
         eng.mpc_solve(s, xr, T, prm, sol=sol, u0=u0, cost=cost, status=status, iters=iters)
 
-    ms, _ = time_device_steps(step, steps, warmup, world, graph=False)   # NCCL gather every step
+    ms, mode = time_device_steps(step, steps, warmup, world, eng=eng)
+    timing = timing_record(steps)
     value = world * n * steps / (ms * 1e-3)
     ms_k, _ = time_device_steps(step_kernel_only, steps, 1, world, eng=eng)
-    g = gathered["g"].cpu().numpy()
+    k_timing = timing_record(steps)
+    g = table.cpu().numpy()
     iters_sum = float(g[:, 5].sum())
-    # governing roofline: the solver's working set (trajectories + gains, 502 floats/problem) streams
-    # through L2/HBM once per sweep, so both an HBM figure (algorithmic I/O bytes) and the executed
-    # flop rate are reported; fp32 peak = SMs x 128 lanes x 2 x max SM clock.
+    # governing roofline: the fp32 FMA pipe (intensity >> machine balance); the executed-flop rate against the
+    # fp32 peak MEASURED in this run, plus the algorithmic I/O rate and the DRAM traffic ncu saw per launch
     peak, peak_src, pk = peaks()
-    achieved = MPC_BYTES * n * steps / (ms_k * 1e-3) / 1e9
-    sm_max = float(pk.get("sm_max_mhz", 1965.0))
-    fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+    achieved_io = MPC_BYTES * n * steps / (ms_k * 1e-3) / 1e9
+    fpk, fpk_src = fp32_peak(eng)
     tfl = mpc_flops(iters_sum / world, n, T) * steps / (ms_k * 1e-3) / 1e12
-    hst, hxr = pinned(st), pinned(xref)
-    hsol = torch.empty((nsol, n), dtype=torch.float32).pin_memory()
-    hu0 = torch.empty((2, n), dtype=torch.float32).pin_memory()
-    hcost = torch.empty(n, dtype=torch.float32).pin_memory()
-    hstat = torch.empty(n, dtype=torch.int32).pin_memory()
-    hit = torch.empty(n, dtype=torch.int32).pin_memory()
-    e_steps = max(2, min(steps, 5))
-    ms_e = time_host_steps(lambda k: eng.mpc_solve_host(hst, hxr, T, prm, sol=hsol, u0=hu0, cost=hcost,
-                                                        status=hstat, iters=hit), e_steps, 1, world)
+    variant = os.environ.get("CRB_MPC_VARIANT", "1")
+    kernel = "crb_mpc_tasks_kernel" if variant != "0" else "crb_mpc_solve_kernel"
+    traffic = traffic_for("mpc") if n == MPC_N else None
     out = dict(metric="MPC solves/sec (T=20, bicycle model, box-constrained DDP to NLP convergence)",
-               value=value, unit="solves/s", ms_per_step=ms / steps,
-               config=dict(workload=f"mpc_T20_{n}_agents_per_gpu", max_iter=MPC_ITER, du_th=MPC_DUTH,
-                           max_ls=MPC_LS, stats_allgather="every step",
-                           l2=f"3 rotating input sets; solver workspace {n * 582 * 4 / 1e6:.0f} MB > 126 MB L2"),
+               value=value, unit="solves/s", ms_per_step=ms / steps, timing=timing,
+               config=dict(workload=label or f"mpc_T20_{n}_agents_per_gpu", agents_per_gpu=n,
+                           global_agents=n * world, max_iter=MPC_ITER, du_th=MPC_DUTH,
+                           max_ls=MPC_LS, stats_allgather="every step, crb_gather_stats inside the graph",
+                           l2="3 rotating input sets; per-CTA slab of stage records resident in L2"),
                solver=dict(mean_iters=iters_sum / (world * n),
                            frac_converged=float(g[:, 4].sum()) / (world * n),
                            mean_cost=float(g[:, 0].sum()) / (world * n),
                            checksum=float(g[:, 6].sum())),
-               roofline=dict(bound="fp32", achieved=tfl, peak=fp32_peak, unit="TFLOP/s",
-                             frac=tfl / fp32_peak, traffic=traffic_for("mpc"),
-                             peak_source=f"148 SM x 128 FMA lanes x 2 x {sm_max:.0f} MHz (nominal; "
-                                         "MEASURED_PEAKS.json has no fp32 non-tensor figure)",
-                             kernel="crb_mpc_solve_kernel", flop_model="see DESIGN.md",
-                             io_gbs=achieved, io_frac_of_hbm=achieved / peak),
-               e2e=dict(value=world * n * e_steps / (ms_e * 1e-3), unit="solves/s",
-                        h2d_bytes_per_step=(4 + 4 * T) * 4 * n, d2h_bytes_per_step=(nsol + 5) * 4 * n))
+               roofline=dict(bound="fp32", achieved=tfl, peak=fpk, unit="TFLOP/s",
+                             frac=tfl / fpk, traffic=traffic, peak_source=fpk_src,
+                             kernel=kernel, flop_model="executed iterations x (T-1) x (470 + 1.2 x 150) flop, DESIGN.md",
+                             solves_per_s_kernel_only=world * n * steps / (ms_k * 1e-3),
+                             ms_per_launch_median=k_timing["ms_per_step_median"],
+                             ms_per_launch_min=k_timing["ms_per_step_min"],
+                             algorithmic_bytes_per_launch=MPC_BYTES * n,
+                             traffic_over_algorithmic=(traffic / (MPC_BYTES * n)) if traffic else None,
+                             io_gbs=achieved_io, io_frac_of_hbm=achieved_io / peak))
+    if with_e2e:
+        hst, hxr = pinned(st), pinned(xref)
+        hsol = torch.empty((nsol, n), dtype=torch.float32).pin_memory()
+        hu0 = torch.empty((2, n), dtype=torch.float32).pin_memory()
+        hcost = torch.empty(n, dtype=torch.float32).pin_memory()
+        hstat = torch.empty(n, dtype=torch.int32).pin_memory()
+        hit = torch.empty(n, dtype=torch.int32).pin_memory()
+        e_steps = max(2, min(steps, 5))
+        ms_e = time_host_steps(lambda k: eng.mpc_solve_host(hst, hxr, T, prm, sol=hsol, u0=hu0, cost=hcost,
+                                                            status=hstat, iters=hit), e_steps, 1, world)
+        out["e2e"] = dict(value=world * n * e_steps / (ms_e * 1e-3), unit="solves/s",
+                          h2d_bytes_per_step=(4 + 4 * T) * 4 * n, d2h_bytes_per_step=(nsol + 5) * 4 * n,
+                          path="crb_mpc_solve_batched_host: pinned host inputs / outputs, 8192-problem chunks "
+                               "over 8 streams")
     if with_cpu and rank == 0:
-        out["cpu_baseline"] = cpu_mpc(st, xref)
+        out["cpu_baseline"] = cpu_mpc(st, xref, gpu_u0=u0[:, :MPC_ACC_N].cpu().numpy(),
+                                      gpu_cost=cost[:MPC_ACC_N].cpu().numpy())
     return out
 
 
-def cpu_mpc(st=None, xref=None, sample=8192):
+MPC_ACC_N = 2048
+
+
+def _f64_solve(args):
+    """Worker of the float64 cross-check (spawned process: numpy only)."""
+    from oracle.ref_mpc_f64 import box_ilqr
+    st, xr, T = args
+    ref = box_ilqr(st.astype(float), xr.reshape(T, 4).T.astype(float), dict(j_tol=0.0, du_th=1e-9, max_iter=200))
+    return float(ref["U"][1, 0]), float(ref["U"][0, 0]), float(ref["cost"])
+
+
+def mpc_accuracy(st, xref, gpu_u0, gpu_cost, T=MPC_T, budget_s=25.0):
+    """How far is the binary32 GPU solve (which replaces IPOPT) from the optimum?  The independent float64
+    statement (oracle/ref_mpc_f64.py, textbook DDP with np.linalg, converged to du 1e-9) on the first agents of
+    the batch, in worker processes; reports max / p99 / median |u0 - u0*| and the relative cost gap."""
+    import multiprocessing as mp
+    m = min(MPC_ACC_N, st.shape[1], gpu_u0.shape[1])
+    jobs = [(st[:, i].copy(), xref[:, i].copy(), T) for i in range(m)]
+    res = []
+    t0 = time.perf_counter()
+    try:
+        ctx = mp.get_context("spawn")
+        with ctx.Pool(min(32, max(1, host_threads() // 2))) as pool:
+            it = pool.imap(_f64_solve, jobs, chunksize=16)
+            for r in it:
+                res.append(r)
+                if time.perf_counter() - t0 > budget_s:
+                    pool.terminate()
+                    break
+    except Exception as exc:   # pragma: no cover
+        return dict(error=str(exc))
+    k = len(res)
+    if k == 0:
+        return dict(error="no float64 solves finished in the budget")
+    r = np.array(res)
+    du = np.maximum(np.abs(r[:, 0] - gpu_u0[0, :k]), np.abs(r[:, 1] - gpu_u0[1, :k]))
+    dc = np.abs(r[:, 2] - gpu_cost[:k]) / np.maximum(np.abs(r[:, 2]), 1e-30)
+    return dict(sample=k, u0_abs_err_max=float(du.max()), u0_abs_err_p99=float(np.percentile(du, 99)),
+                u0_abs_err_median=float(np.median(du)), cost_rel_gap_max=float(dc.max()),
+                cost_rel_gap_p99=float(np.percentile(dc, 99)),
+                reference="oracle/ref_mpc_f64.py box_ilqr (float64, du_th 1e-9): the KKT point of the reference NLP; "
+                          "the reference's own IPOPT solve is capped at 50 ms and unreproducible (mpc:328)",
+                seconds=time.perf_counter() - t0)
+
+
+def cpu_mpc(st=None, xref=None, sample=8192, gpu_u0=None, gpu_cost=None):
     from cpprobotics_b200 import synth
     from oracle import oracle as O
     T = MPC_T
@@ -559,18 +815,24 @@ def cpu_mpc(st=None, xref=None, sample=8192):
         xref, _ = synth.mpc_xref_numpy(st, pind, T, course=course)
     st, xref = np.ascontiguousarray(st[:, :sample]), np.ascontiguousarray(xref[:, :sample])
     prm = O.mpc_params(max_iter=MPC_ITER, du_th=MPC_DUTH, max_ls=MPC_LS)
+    CPU_SPREAD.clear()
     thr, mask = tuned_threads(lambda c: O.mpc_solve_batched(st, xref, T, prm, nthreads=c))
     v, calls, el = cpu_time(lambda: O.mpc_solve_batched(st, xref, T, prm, nthreads=thr), sample,
                             budget_s=5.0)
+    spread = CPU_SPREAD[-1]
     st1, xr1 = np.ascontiguousarray(st[:, :256]), np.ascontiguousarray(xref[:, :256])
-    v1, _, _ = cpu_time(lambda: O.mpc_solve_batched(st1, xr1, T, prm, nthreads=1), 256, budget_s=1.0)
+    v1, _, _ = cpu_time(lambda: O.mpc_solve_batched(st1, xr1, T, prm, nthreads=1), 256, budget_s=1.0, min_passes=3)
     vb = best_effort(lambda: O.mpc_solve_batched(st, xref, T, prm, nthreads=thr), sample)
-    return dict(value=v, unit="solves/s", cores=thr, kind="port", single_core_value=v1, best_effort_value=vb,
-                sample=f"{calls} x {sample} agents (first {sample} of the GPU batch), T={T}, "
-                       f"oracle/crb_oracle_mpc.c same algorithm, OpenMP {thr} threads (fastest of 1/4..1 x the "
-                       f"{mask}-cpu mask), {el:.1f} s; "
-                       "the reference's CppAD+IPOPT solve cannot be built here (its own budget is "
-                       "50 ms per solve, model_predictive_control.cpp:328)")
+    out = dict(value=v, unit="solves/s", cores=thr, kind="port", single_core_value=v1, best_effort_value=vb,
+               spread=spread,
+               sample=f"median of {calls} passes x {sample} agents (first {sample} of the GPU batch), T={T}, "
+                      f"oracle/crb_oracle_mpc.c same algorithm, OpenMP {thr} threads bound to cores (best median of 5 "
+                      f"passes at 1/4..1 x the {mask}-cpu mask), {el:.1f} s; "
+                      "the reference's CppAD+IPOPT solve cannot be built here (its own budget is "
+                      "50 ms per solve, model_predictive_control.cpp:328)")
+    if gpu_u0 is not None:
+        out["accuracy_vs_float64_optimum"] = mpc_accuracy(st, xref, gpu_u0, gpu_cost)
+    return out
 
 
 def bench_ekf_multistep(eng, rank, world, steps, warmup):
@@ -652,13 +914,12 @@ def bench_lqr(eng, rank, world, steps, warmup, with_cpu):
                               eng=eng)
     mean_it = float(it.float().mean().item())
     flops = mean_it * 2.0 * (5 * 64 + 2 * 16 + 4 + 16) * n * steps    # 5 4x4x4 + 2 4x4x1 + outer + misc per iter
-    sm_max = float(peaks()[2].get("sm_max_mhz", 1965.0))
-    fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+    fpk, fpk_src = fp32_peak(eng)
     out = dict(metric="DARE/LQR gains per second (lqr_steer_control solve_DARE+dlqr, nx=4)",
                value=world * n * steps / (ms * 1e-3), unit="solves/s", ms_per_step=ms / steps,
                config=dict(workload="lqr_dlqr_2^20_agents_per_gpu", mean_dare_iters=mean_it),
-               roofline=dict(bound="fp32", achieved=flops / (ms * 1e-3) / 1e12, peak=fp32_peak, unit="TFLOP/s",
-                             frac=flops / (ms * 1e-3) / 1e12 / fp32_peak, traffic=None,
+               roofline=dict(bound="fp32", achieved=flops / (ms * 1e-3) / 1e12, peak=fpk, unit="TFLOP/s",
+                             frac=flops / (ms * 1e-3) / 1e12 / fpk, traffic=None, peak_source=fpk_src,
                              note="no FMA contraction by design (bit-exact with the reference arithmetic): "
                                   "FMUL+FADD pairs, so 0.5 is the ceiling of this fraction",
                              kernel="crb_lqr_dlqr_kernel<4,1>"))
@@ -673,25 +934,63 @@ def bench_lqr(eng, rank, world, steps, warmup, with_cpu):
     return out
 
 
+# sources that define each profiled kernel: profiles/traffic.json carries their hash, so a DRAM-traffic figure
+# captured for an older kernel is recognised as stale and NOT reported
+KERNEL_SOURCES = {
+    "ekf": ["cpprobotics_b200/csrc/crb_ekf.cu", "cpprobotics_b200/csrc/crb_common.cuh"],
+    "pf": ["cpprobotics_b200/csrc/crb_pf.cu", "cpprobotics_b200/csrc/crb_common.cuh"],
+    "mpc": ["cpprobotics_b200/csrc/crb_mpc_tasks.cu", "cpprobotics_b200/csrc/crb_mpc_core.cuh",
+            "cpprobotics_b200/csrc/crb_mpc.cu"],
+}
+
+
+def kernel_stamp(name):
+    import hashlib
+    h = hashlib.sha256()
+    for rel in KERNEL_SOURCES[name]:
+        with open(os.path.join(ROOT, rel), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+TRAFFIC_STALE = []
+
+
 def traffic_for(name):
-    """DRAM bytes per launch from the committed ncu --set full capture (profiles/traffic.json)."""
+    """DRAM bytes per launch from the committed ncu --set full capture (profiles/traffic.json), only if the capture
+    was taken from the kernel sources this run was built from (hash stamp); otherwise None (and noted)."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(p):
-        try:
-            return json.load(open(p)).get(name)
-        except Exception:
-            return None
+    try:
+        rec = json.load(open(p)).get(name)
+    except Exception:
+        return None
+    if isinstance(rec, dict):
+        if rec.get("stamp") == kernel_stamp(name):
+            return rec.get("bytes")
+        TRAFFIC_STALE.append(name)
+        return None
+    TRAFFIC_STALE.append(name)       # unstamped (round-1 format): cannot be trusted for the current kernel
     return None
 
 
 # =========================================================================================================
+def nest(head, res, key, sub):
+    """Copy res[sub][key] (a workload's roofline / e2e / cpu_baseline) under head[key][sub]."""
+    if sub in res and key in res[sub] and isinstance(head.get(key), dict):
+        head[key][sub.replace("^", "")] = res[sub][key]
+
+
 def run_ours(args):
     import torch
     from cpprobotics_b200 import Engine
     rank, world, local = dist_setup(args.gpus)
     eng = Engine(local)
+    comm_setup(eng, rank, world)
     res = {}
     cpu = (not args.no_cpu) and world == 1     # cpu_baseline: rank 0 at N = 1 only (the contract)
+    restore = (lambda: None)
+    if cpu:
+        restore, pin_note = cpu_pin_one_numa_node()
     with ClockSampler(local) as clk:
         head = bench_ekf(eng, rank, world, args.steps, args.warmup, with_cpu=cpu)
         if args.workload in ("all", "pf"):
@@ -705,28 +1004,61 @@ def run_ours(args):
         if args.workload in ("all", "lqr"):
             res["lqr"] = bench_lqr(eng, rank, world, max(3, args.steps // 5), 3, with_cpu=cpu)
         if args.workload in ("all", "mpc"):
+            # BASELINE configs[3]: 65 536 agents per GPU (weak scaling like the headline)
             res["mpc"] = bench_mpc(eng, rank, world, max(3, args.steps // 5), max(1, args.warmup // 3),
                                    with_cpu=cpu)
-            # the same solver with the machine filled (BASELINE config 5's 2^20 agents on one GPU): the
-            # 2^16-agent contract size occupies 20 % of the resident-warp capacity
-            big = bench_mpc(eng, rank, world, 3, 1, with_cpu=False, n=1 << 20)
-            big["metric"] += ", 2^20 agents per GPU"
-            res["mpc_2^20_agents"] = big
+            # BASELINE configs[4] AS WRITTEN: 2^20 agents in total, sharded over the N GPUs (strong scaling:
+            # 2^20 / N per GPU), index-addressed shards, one all-gather of the cost statistics per call
+            tot = 1 << 20
+            res["mpc_config5"] = bench_mpc(eng, rank, world, 3, 1, with_cpu=False, n=tot // world,
+                                           label=f"mpc_T20_2^20_agents_sharded_over_{world}_gpus "
+                                                 f"({tot // world} per GPU; BASELINE.json configs[4])",
+                                           with_e2e=(world == 1))
+            c5 = res["mpc_config5"]
+            c5["config"]["scaling"] = "strong (total fixed at 2^20)"
+            c5["per_gpu_solves_per_s"] = c5["value"] / world
+            c5["roofline"]["frac_of_n_gpus_peak"] = c5["roofline"]["frac"]     # per-GPU flop rate / per-GPU peak
+    restore()
+    cfg = {"workload": "ekf_2^20_agents_1_step_per_gpu (BASELINE.json configs[1])",
+           "agents_per_gpu": EKF_N, "global_agents": EKF_N * world,
+           "l2": "3 rotating buffer sets, 303 MB of inputs > 126 MB L2",
+           "collective": "one all-gather of 8 doubles per rank (libcrb crb_gather_stats, NCCL) inside the captured "
+                         "graph, once per replay of K steps",
+           "launch": head["launch_mode"], "timing": head["timing"]}
     line = {
         "metric": "EKF updates/sec (4-state/2-obs predict+update, batched)",
         "value": head["value"], "unit": "updates/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": head["ms"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "ekf_2^20_agents_1_step_per_gpu (BASELINE.json configs[1])",
-                   "agents_per_gpu": EKF_N, "global_agents": EKF_N * world,
-                   "l2": "3 rotating buffer sets, 303 MB of inputs > 126 MB L2",
-                   "collective": "one all-gather of 8 doubles per rank inside the timed region",
-                   "launch": head["launch_mode"]},
+        "config": cfg,
         "clocks": clk.summary(), "e2e": head["e2e"], "gpu_launches": head["launches"],
         "roofline": head["roofline"],
     }
     if "cpu_baseline" in head:
         line["cpu_baseline"] = head["cpu_baseline"]
+        line["cpu_baseline"]["pinning"] = pin_note
+    # BASELINE.json's metric is "EKF updates/sec & MPC solves/sec ...": the MPC (and PF) figures of this run are part
+    # of the record the driver parses, not an appendix
+    for sub in ("mpc", "pf", "mpc_config5"):
+        for key in ("roofline", "e2e", "cpu_baseline"):
+            nest(line, res, key, sub)
+    if "mpc" in res:
+        cfg["mpc_solves_per_s"] = res["mpc"]["value"]
+        cfg["mpc_workload"] = res["mpc"]["config"]["workload"] + " (BASELINE.json configs[3])"
+        cfg["mpc_ms_per_step"] = res["mpc"]["ms_per_step"]
+        cfg["mpc_solver"] = res["mpc"]["solver"]
+        if "accuracy_vs_float64_optimum" in res["mpc"].get("cpu_baseline", {}):
+            cfg["mpc_accuracy_vs_float64_optimum"] = res["mpc"]["cpu_baseline"]["accuracy_vs_float64_optimum"]
+    if "mpc_config5" in res:
+        c5 = res["mpc_config5"]
+        cfg["mpc_config5"] = dict(workload=c5["config"]["workload"], solves_per_s=c5["value"],
+                                  per_gpu_solves_per_s=c5["per_gpu_solves_per_s"], ms_per_step=c5["ms_per_step"],
+                                  frac_of_fp32_peak=c5["roofline"]["frac"], n_gpus=world)
+    if "pf" in res:
+        cfg["pf_particles_per_s"] = res["pf"]["value"]
+        cfg["pf_workload"] = res["pf"]["config"]["workload"] + " (BASELINE.json configs[2])"
+    if TRAFFIC_STALE:
+        cfg["traffic_stale"] = sorted(set(TRAFFIC_STALE))
     if res:
         line["extra"] = res
     if rank == 0:
@@ -743,6 +1075,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    restore, pin_note = cpu_pin_one_numa_node()
     from oracle import oracle as O
     from cpprobotics_b200 import synth
     n = EKF_N
@@ -750,10 +1083,13 @@ def run_reference(args):
     thr, mask = tuned_threads(lambda c: O.ekf_step_batched(x, P, z, u, nthreads=c, inplace=True))
     for _ in range(args.warmup):
         O.ekf_step_batched(x, P, z, u, nthreads=thr, inplace=True)
-    t0 = time.perf_counter()
+    ts = []
     for _ in range(args.steps):
+        t0 = time.perf_counter()
         O.ekf_step_batched(x, P, z, u, nthreads=thr, inplace=True)
-    el = time.perf_counter() - t0
+        ts.append(time.perf_counter() - t0)
+    ts = np.array(ts)
+    el = float(ts.sum())
     v = n * args.steps / el
     vb = best_effort(lambda: O.ekf_step_batched(x, P, z, u, nthreads=thr, inplace=True), n)
     line = {
@@ -764,15 +1100,20 @@ def run_reference(args):
         "config": {"workload": "ekf_2^20_agents_1_step_per_gpu (BASELINE.json configs[1])",
                    "agents_per_gpu": EKF_N},
         "cpu_baseline": {"value": v, "unit": "updates/s", "cores": thr, "kind": "port", "best_effort_value": vb,
+                         "pinning": pin_note,
+                         "spread": dict(passes=int(ts.size), fastest=n / ts.min(), slowest=n / ts.max(),
+                                        median=n / float(np.median(ts))),
                          "sample": f"{args.steps} x {n} agents x 1 step per timed step, oracle/crb_oracle.c "
-                                   f"(-O2 -ffp-contract=off), OpenMP {thr} threads (fastest of 1/4..1 x the "
-                                   f"{mask}-cpu mask)"},
+                                   f"(-O2 -ffp-contract=off), OpenMP {thr} threads bound to cores (best median of 5 "
+                                   f"passes at 1/4..1 x the {mask}-cpu mask)"},
         "e2e": {"value": v, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     if args.workload in ("all", "pf"):
-        line.setdefault("extra", {})["pf"] = cpu_pf()
+        line["cpu_baseline"]["pf"] = cpu_pf()
     if args.workload in ("all", "mpc"):
-        line.setdefault("extra", {})["mpc"] = cpu_mpc()
+        line["cpu_baseline"]["mpc"] = cpu_mpc()
+        line["config"]["mpc_solves_per_s"] = line["cpu_baseline"]["mpc"]["value"]
+    restore()
     print(json.dumps(line), flush=True)
 
 

@@ -325,6 +325,12 @@ class Engine:
                                                   int(buf.numel())), "crb_comm_allreduce_sum_f64")
         return buf
 
+    def probe_fp32_peak(self) -> float:
+        """Measured non-tensor fp32 FMA rate of this GPU, TFLOP/s (crb_probe.cu)."""
+        v = C.c_double()
+        check(self.lib.crb_probe_fp32_peak(self.ctx, C.byref(v)), "crb_probe_fp32_peak")
+        return float(v.value)
+
     # ---- stats ------------------------------------------------------------------------------------
     def stats_reduce(self, values, status=None, iters=None, i0: int = 0, out=None):
         """Per-GPU summary of a per-agent f32 array -> float64 CUDA tensor of CRB_STATS_LEN."""

@@ -294,6 +294,11 @@ int crb_comm_allreduce_sum_f64(crb_ctx* ctx, double* buf_dev, int64_t count);
 int crb_stats_reduce(crb_ctx* ctx, int64_t n, int64_t i0, const float* values,
                      const int32_t* status, const int32_t* iters, double* stats_dev);
 
+/* ---- measurement aid ---------------------------------------------------------------------------------- */
+/* Non-tensor binary32 FMA rate of the context's device at its current clocks, in TFLOP/s (best of 5 launches of
+ * a register-only FFMA kernel, synchronous).  The denominator of the MPC / LQR roofline fractions. */
+int crb_probe_fp32_peak(crb_ctx* ctx, double* tflops_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -44,6 +44,12 @@ def use_library(which: str = "faithful") -> bool:
             want = FAST_LIB_PATH
         else:
             ok = False
+    if which == "O0":   # BASELINE.md B0 "as shipped" (-O0, the reference's CMakeLists.txt:5): a timing arm only
+        p0 = os.path.join(_HERE, "lib", "liboracle_O0.so")
+        if os.path.exists(p0):
+            want = p0
+        else:
+            ok = False
     _libs[LIB_PATH] = _lib
     LIB_PATH = want
     _lib = _libs.get(want)

@@ -81,10 +81,18 @@ def captures(tag):
         ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
         t = [float(d[ir].replace(",", "")) * TO_BYTES[units[ir]] + float(d[iw].replace(",", "")) * TO_BYTES[units[iw]]
              for d in data]
-        traffic[w] = sum(t) / len(t)
+        sys.path.insert(0, ROOT)
+        import bench
+        traffic[w] = {"bytes": sum(t) / len(t), "stamp": bench.kernel_stamp(w), "kernel": name, "capture": tag}
         out.append("")
     open(os.path.join(PROF, f"{tag}_ncu_summary.md"), "w").write("\n".join(out))
-    json.dump(traffic, open(os.path.join(PROF, "traffic.json"), "w"), indent=1)
+    path = os.path.join(PROF, "traffic.json")
+    try:
+        merged = json.load(open(path))
+    except Exception:
+        merged = {}
+    merged.update(traffic)
+    json.dump(merged, open(path, "w"), indent=1)
     return traffic
 
 
