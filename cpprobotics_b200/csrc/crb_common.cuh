@@ -172,47 +172,61 @@ __device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
 // different ulps) cannot meet a per-particle 1e-5 gate on the weights.  glibc >= 2.28 computes sinf / cosf
 // in BINARY64: x = (double)y, one multiply-subtract range reduction by pi/2 (exact to 33 bits for |y| < 120),
 // a degree-7/8 polynomial, one final rounding to float (sysdeps/ieee754/flt-32/s_sinf.c, s_cosf.c,
-// sincosf.h, s_sincosf_data.c).  Every operation is an IEEE binary64 multiply or add, which the B200's FP64
-// pipe reproduces bit for bit (this TU is built -fmad=false), so the routine below returns the host's bits:
-// checked against the host libm on 3.2e8 floats in |y| < 120 (oracle/crb_oracle.c:crb_oracle_libm_sincosf,
-// tests/test_oracle_ekf.py): sin identical, cos differs on 2e-8 of the inputs where glibc's FMA build
-// (ifunc-selected on hosts with FMA) rounds an intermediate differently.  |y| >= 120 (glibc's table-driven
-// reduce_large) is not restated: CUDA's sincosf is used there (no BASELINE workload comes near it).
+// sincosf.h, s_sincosf_data.c).  On x86-64 hosts with FMA (every server CPU of the last decade) glibc's ifunc
+// picks the build of those files compiled with -mfma, in which each a + b * c of the source is ONE fused
+// operation: that is what is restated here with explicit fma(), operation for operation, and the B200's FP64
+// pipe (IEEE DFMA / DMUL) reproduces it bit for bit.  Checked against the host libm on 3.2e8 floats in
+// |y| < 120 (oracle/crb_oracle.c:crb_oracle_libm_sincosf, tests/test_oracle_ekf.py): sin AND cos identical on
+// every one of them.  (On a host without FMA, glibc's plain build differs from this on 2e-8 of the inputs, by
+// one ulp.)  |y| >= 120 (glibc's table-driven reduce_large) is not restated: CUDA's sincosf is used there (no
+// BASELINE workload comes near it).  17 FP64 operations + 3 conversions per call.
+static __device__ __noinline__ float2 crb_sincosf_large(float y) {  // by value: no address-taken locals at the call site
+  float s, c;
+  sincosf(y, &s, &c);
+  return make_float2(s, c);
+}
+// x with the sign flipped when neg != 0 (x * -1.0 without occupying the FP64 pipe)
+__device__ __forceinline__ double crb_flip(double x, int neg) {
+  return __hiloint2double(__double2hiint(x) ^ (neg ? (int)0x80000000 : 0), __double2loint(x));
+}
 __device__ __forceinline__ void crb_sincosf_libm(float y, float& sn, float& cs) {
   const unsigned top = (__float_as_uint(y) >> 20) & 0x7ffu;
-  if (top >= 0x42fu) {  // |y| >= 120, inf, nan
-    sincosf(y, &sn, &cs);
+  if (top >= 0x42fu) {  // |y| >= 120, inf, nan: out of line (CUDA's Payne-Hanek path is long)
+    const float2 sc = crb_sincosf_large(y);
+    sn = sc.x;
+    cs = sc.y;
     return;
   }
   double x = (double)y;
   int n = 0;
-  double sgn = 1.0;
   if (top >= 0x3f4u) {  // |y| >= pi/4 (abstop12(0x1.921FB6p-1f) = 0x3f4): reduce_fast
     const double r = x * 0x1.45F306DC9C883p+23;
     n = ((int)r + 0x800000) >> 24;
-    x = x - (double)n * 0x1.921FB54442D18p0;
-    sgn = ((n + 1) & 2) ? -1.0 : 1.0;  // sign[n & 3] = {1, -1, -1, 1}
+    x = fma(-(double)n, 0x1.921FB54442D18p0, x);
   } else if (top < 0x398u) {  // |y| < 2^-12
     sn = y;
     cs = 1.0f;
     return;
   }
   const double x2 = x * x;
-  const double q = (n & 2) ? -1.0 : 1.0;  // second table entry: cosine coefficients negated
-  const double xs = x * sgn;
+  const int neg_s = (n + 1) & 2;  // sign[n & 3] = {1, -1, -1, 1}
+  const int neg_c = n & 2;        // second table entry: cosine coefficients negated
+  const double xs = crb_flip(x, neg_s);
   // sine polynomial on xs (its coefficients are the same in both table entries)
   const double x3 = xs * x2;
-  const double s1 = 0x1.1107605230bc4p-7 + x2 * -0x1.994eb3774cf24p-13;
+  const double s1 = fma(x2, -0x1.994eb3774cf24p-13, 0x1.1107605230bc4p-7);
   const double x7 = x3 * x2;
-  const double sp = xs + x3 * -0x1.555545995a603p-3;
-  const float ps = (float)(sp + x7 * s1);
-  // cosine polynomial
+  const double sp = fma(x3, -0x1.555545995a603p-3, xs);
+  const float ps = (float)fma(x7, s1, sp);
+  // cosine polynomial: negating all five coefficients negates every intermediate and the result exactly, so
+  // the polynomial is evaluated with the first table entry and the sign applied to the rounded float
   const double x4 = x2 * x2;
-  const double c2 = q * -0x1.6c087e89a359dp-10 + x2 * (q * 0x1.99343027bf8c3p-16);
-  const double c1 = q * 0x1p0 + x2 * (q * -0x1.ffffffd0c621cp-2);
+  const double c2 = fma(x2, 0x1.99343027bf8c3p-16, -0x1.6c087e89a359dp-10);
+  const double c1 = fma(x2, -0x1.ffffffd0c621cp-2, 1.0);
   const double x6 = x4 * x2;
-  const double cp = c1 + x4 * (q * 0x1.55553e1068f19p-5);
-  const float pc = (float)(cp + x6 * c2);
+  const double cp = fma(x4, 0x1.55553e1068f19p-5, c1);
+  const float pc0 = (float)fma(x6, c2, cp);
+  const float pc = __int_as_float(__float_as_int(pc0) ^ (neg_c ? (int)0x80000000 : 0));
   // sinf uses the sine polynomial for even n, cosf for odd n (and vice versa)
   sn = (n & 1) ? pc : ps;
   cs = (n & 1) ? ps : pc;

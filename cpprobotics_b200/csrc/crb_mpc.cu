@@ -753,7 +753,10 @@ extern "C" int crb_mpc_solve_batched_host(crb_ctx* ctx, int64_t n, int T, const 
   // its whole (single) wave on the link first (measured: 34.7 M solves/s fully zero-copy vs 37.2 staged).
   float *msol = nullptr, *mu0 = nullptr, *mcost = nullptr;
   int32_t *mstat = nullptr, *mit = nullptr;
-  const bool direct_out = crb_zero_copy_enabled() && crb_host_mapped(sol, &msol) &&
+  // (only the first-generation kernel: its warps store 32 consecutive problems per instruction, whereas the task
+  // kernel retires problems in completion order, i.e. as scattered 4-byte stores, which PCIe turns into one
+  // transaction each: measured 4.2 M solves/s instead of 45 M)
+  const bool direct_out = mpc_variant() == 0 && crb_zero_copy_enabled() && crb_host_mapped(sol, &msol) &&
                           crb_host_mapped(u0, &mu0) && crb_host_mapped(cost, &mcost) &&
                           crb_host_mapped(status, &mstat) && crb_host_mapped(iters, &mit);
   int slot = 0;

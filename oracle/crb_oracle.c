@@ -511,8 +511,8 @@ void crb_oracle_dlqr_batched(int64_t n, int nx, int nu, const float* A, const fl
  * glibc >= 2.28: sysdeps/ieee754/flt-32/s_sinf.c, s_cosf.c, sincosf.h (reduce_fast, sinf_poly),
  * s_sincosf_data.c (__sincosf_table).  Third-party code that is not under /root/reference: the reference
  * reaches it through std::sin / std::cos on floats (src/extended_kalman_filter.cpp:29-33, :41-45;
- * src/particle_filter.cpp:33-37).  Everything is binary64 multiply / add with one final rounding to float, so
- * the GPU's FP64 pipe can reproduce it.  Pinned by tests/test_oracle_ekf.py against THIS host's libm (the
+ * src/particle_filter.cpp:33-37).  Everything is binary64 multiply / add / fused multiply-add with one final
+ * rounding to float, so the GPU's FP64 pipe can reproduce it.  Pinned by tests/test_oracle_ekf.py against THIS host's libm (the
  * oracle's EKF / PF restatements keep calling libm itself, like the reference).  |y| >= 120 (reduce_large) is
  * not restated: libm is called. */
 static uint32_t ls_abstop12(float x) {
@@ -521,6 +521,7 @@ static uint32_t ls_abstop12(float x) {
   return (u >> 20) & 0x7ff;
 }
 void crb_oracle_libm_sincosf(float y, float* sn, float* cs) {
+  /* the -mfma build of glibc's sources (what the ifunc selects on hosts with FMA): every a + b * c is fused */
   const uint32_t top = ls_abstop12(y);
   if (top >= 0x42f) { /* |y| >= 120, inf, nan */
     *sn = sinf(y);
@@ -529,31 +530,30 @@ void crb_oracle_libm_sincosf(float y, float* sn, float* cs) {
   }
   double x = (double)y;
   int n = 0;
-  double sgn = 1.0;
   if (top >= 0x3f4) { /* |y| >= pi/4: reduce_fast, hpi_inv prescaled by 2^24 */
     const double r = x * 0x1.45F306DC9C883p+23;
     n = ((int32_t)r + 0x800000) >> 24;
-    x = x - (double)n * 0x1.921FB54442D18p0;
-    sgn = ((n + 1) & 2) ? -1.0 : 1.0; /* sign[n & 3] = {1, -1, -1, 1} */
+    x = fma(-(double)n, 0x1.921FB54442D18p0, x);
   } else if (top < 0x398) { /* |y| < 2^-12 */
     *sn = y;
     *cs = 1.0f;
     return;
   }
   const double x2 = x * x;
-  const double q = (n & 2) ? -1.0 : 1.0; /* __sincosf_table[1]: cosine coefficients negated */
+  const double sgn = ((n + 1) & 2) ? -1.0 : 1.0; /* sign[n & 3] = {1, -1, -1, 1} */
+  const double q = (n & 2) ? -1.0 : 1.0;         /* __sincosf_table[1]: cosine coefficients negated */
   const double xs = x * sgn;
   const double x3 = xs * x2;
-  const double s1 = 0x1.1107605230bc4p-7 + x2 * -0x1.994eb3774cf24p-13;
+  const double s1 = fma(x2, -0x1.994eb3774cf24p-13, 0x1.1107605230bc4p-7);
   const double x7 = x3 * x2;
-  const double sp = xs + x3 * -0x1.555545995a603p-3;
-  const float ps = (float)(sp + x7 * s1);
+  const double sp = fma(x3, -0x1.555545995a603p-3, xs);
+  const float ps = (float)fma(x7, s1, sp);
   const double x4 = x2 * x2;
-  const double c2 = q * -0x1.6c087e89a359dp-10 + x2 * (q * 0x1.99343027bf8c3p-16);
-  const double c1 = q * 0x1p0 + x2 * (q * -0x1.ffffffd0c621cp-2);
+  const double c2 = fma(x2, q * 0x1.99343027bf8c3p-16, q * -0x1.6c087e89a359dp-10);
+  const double c1 = fma(x2, q * -0x1.ffffffd0c621cp-2, q);
   const double x6 = x4 * x2;
-  const double cp = c1 + x4 * (q * 0x1.55553e1068f19p-5);
-  const float pc = (float)(cp + x6 * c2);
+  const double cp = fma(x4, q * 0x1.55553e1068f19p-5, c1);
+  const float pc = (float)fma(x6, c2, cp);
   *sn = (n & 1) ? pc : ps;
   *cs = (n & 1) ? ps : pc;
 }
