@@ -595,39 +595,32 @@ def bench_pf(eng, rank, world, steps, warmup, with_cpu):
 
 
 def bench_pf_iteration(eng, rank, world, steps, warmup):
-    """Row f-2: one complete filter iteration per step = predict+weight (:81-102), normalise + estimate +
-    covariance (:104-107, host-visible results => one sync per step) and low-variance resampling
-    (:111-148, forced every step with nth = n).  Not graph-captured (the estimate returns to the host)."""
+    """Row f-2: one complete filter iteration per step = crb_pf_step: predict+weight (:81-102), normalise +
+    estimate + covariance (:104-107), Neff and low-variance resampling decided on the device (:120-148, forced
+    every step with nth = n), particle arrays ping-ponged.  No host round trip, so the K iterations are captured
+    in a CUDA graph like every other workload.  With world > 1 the filter is sharded: the weight sum and the
+    moments are all-reduced inside libcrb and particles are not resampled across GPUs."""
     import torch
     from cpprobotics_b200 import synth
     n = 1 << 20
     dev = torch.device("cuda", torch.cuda.current_device())
     px, pw, noise = (torch.from_numpy(a).to(dev) for a in synth.pf_inputs(n, i0=rank * n, n_total=world * n))
     lm = synth.pf_landmarks(PF_LM)
-    tmp = torch.empty_like(px)
-    st = {"resampled": 0}
+    bufs = [px, torch.empty_like(px)]
+    res = torch.zeros(24, dtype=torch.float64, device=dev)
 
     def step(k):
-        eng.pf_predict_weight(px, pw, noise, lm)
-        eng.pf_estimate(px, pw)
-        did, _ = eng.pf_resample(px, pw, seed=k, nth=float(n), px_tmp=tmp)
-        st["resampled"] += int(did)
-    for k in range(warmup):
-        step(k)
-    barrier_sync(world)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    eng.bind_current_stream()
-    e0.record()
-    for k in range(steps):
-        step(warmup + k)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = max_over_ranks(e0.elapsed_time(e1), world)
+        eng.pf_step(bufs[k & 1], pw, bufs[(k + 1) & 1], noise, lm, resample_seed=k, nth=float(n), result=res)
+    steps += steps & 1          # an even number of steps per replay keeps the ping-pong consistent across replays
+    ms, mode = time_device_steps(step, steps, warmup + (warmup & 1), world, eng=eng)
+    r = res.cpu().numpy()
     return dict(metric="PF filter iterations (predict+weight, estimate, resample) x particles per second",
                 value=world * n * steps / (ms * 1e-3), unit="particles/s", ms_per_step=ms / steps,
-                config=dict(workload="pf_full_iteration_2^20_particles_per_gpu",
-                            resampled_steps=st["resampled"], steps=steps,
-                            note="estimate copies xEst/PEst to the host every step (one stream sync per step)"))
+                timing=timing_record(steps),
+                config=dict(workload="pf_full_iteration_2^20_particles_per_gpu (crb_pf_step)", steps=steps,
+                            resampled_last_step=bool(r[22] == 1.0), neff_last_step=float(r[21]), launch=mode,
+                            note="6 kernels per iteration, no host synchronisation, no device copy; round 1 was 10 "
+                                 "kernels, 2 synchronous read-backs and a 16 MB copy (135 us)"))
 
 
 def cpu_pf(host=None, lm=None):

@@ -16,6 +16,7 @@ CRB_OK = 0
 CRB_ERR_NO_DEVICE = -2
 CRB_STATS_LEN = 8
 CRB_COMM_ID_BYTES = 128
+CRB_PF_RESULT_LEN = 24
 CRB_PF_MAX_LANDMARKS = 64
 CRB_MPC_MAX_T = 32
 
@@ -83,6 +84,9 @@ PROTOTYPES = {
                                   C.c_void_p, C.c_void_p]),
     "crb_pf_resample": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_uint64, C.c_float, C.c_void_p, C.c_void_p]),
+    "crb_pf_step": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                              C.c_void_p, C.c_int, C.POINTER(PfParams), C.c_void_p, C.c_uint64, C.c_float,
+                              C.c_void_p]),
     "crb_mpc_default_params": (None, [C.POINTER(MpcParams)]),
     "crb_mpc_solve_batched": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.POINTER(MpcParams), C.c_void_p, C.c_void_p,

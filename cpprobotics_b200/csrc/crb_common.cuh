@@ -84,6 +84,7 @@ int crb_ctx_pipe_reserve(crb_ctx* ctx, int slot, size_t bytes);
 int crb_ctx_scratch_reserve(crb_ctx* ctx, size_t bytes);
 int crb_ctx_mpc_ws_reserve(crb_ctx* ctx, size_t bytes);
 extern "C" int crb_comm_destroy(crb_ctx* ctx);
+extern "C" int crb_comm_allreduce_sum_f64(crb_ctx* ctx, double* buf_dev, int64_t count);
 
 // Strided host<->device block copy for the *_host pipelines.  Measured on this platform
 // (scripts/pcie_probe.py + bench e2e): plain 1-D copies reach 48 (H2D) / 57 (D2H) GB/s, one

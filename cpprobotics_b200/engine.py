@@ -213,6 +213,27 @@ class Engine:
             C.c_float(n // 2 if nth is None else nth), C.addressof(did), C.addressof(neff)), "crb_pf_resample")
         return bool(did.value), neff.value
 
+    def pf_step(self, px, pw, px_next, noise, landmarks, params: Optional[PfParams] = None, seed: int = 0,
+                uniforms=None, resample_seed: int = 0, nth: Optional[float] = None, result=None):
+        """One complete filter iteration on the device (crb_pf_step): predict + weight on px / pw, estimate,
+        resampling decided on the device, next particle set in px_next.  Returns the float64 CUDA result tensor
+        [xEst(4) | PEst(16, column-major) | sum_w | Neff | resampled | sum wn^2]; nothing is synchronised."""
+        n = int(px.shape[-1])
+        _shape(px, 4, n, "px"); _shape(px_next, 4, n, "px_next")
+        lm = np.ascontiguousarray(landmarks, np.float32).reshape(-1, 3)
+        prm = params if params is not None else pf_default_params()
+        if result is None:
+            result = torch.zeros(_lib.CRB_PF_RESULT_LEN, dtype=torch.float64, device=px.device)
+        check(self.lib.crb_pf_step(
+            self.ctx, n, _ptr(px, np.float32, device=True, name="px"), _ptr(pw, np.float32, device=True, name="pw"),
+            _ptr(px_next, np.float32, device=True, name="px_next"),
+            _ptr(noise, np.float32, device=True, name="noise"), C.c_uint64(int(seed)),
+            lm.ctypes.data if lm.size else None, int(lm.shape[0]), C.byref(prm),
+            _ptr(uniforms, np.float32, device=True, name="uniforms"), C.c_uint64(int(resample_seed)),
+            C.c_float(n // 2 if nth is None else nth), _ptr(result, np.float64, device=True, name="result")),
+            "crb_pf_step")
+        return result
+
     # ---- MPC --------------------------------------------------------------------------------------
     def _mpc(self, fn, dev, x0, xref, T, params, u_init, sol, u0, cost, status, iters):
         n = int(x0.shape[-1])

@@ -165,7 +165,12 @@ int crb_pf_predict_weight_batched_host(crb_ctx* ctx, int64_t n, float* px, float
  *   pw is normalised in place (pw / pw.sum(), :104); xEst[4] = px * pw (:106);
  *   PEst[16] (column-major) = sum_i pw_i (px_i - xEst)(px_i - xEst)^T (:59-71, :107).
  * Reductions are done in double on the device (deterministic two-pass tree), so results are
- * independent of the launch geometry.  sum_w_out (optional) receives the pre-normalisation sum. */
+ * independent of the launch geometry.  sum_w_out (optional) receives the pre-normalisation sum.
+ * On a context with a communicator (particles sharded over GPUs) the sums run over ALL ranks (two small
+ * all-reduces): every rank normalises by the global weight sum and gets the global estimate.
+ * Weights whose exponent underflows are floored at w * 2^-126 by the default predict+weight kernel (the
+ * reference's running float product would go denormal or 0): if EVERY particle is far from the observations the
+ * reference divides 0 / 0 (:104) whereas this engine returns uniform weights - watch sum_w. */
 int crb_pf_estimate(crb_ctx* ctx, int64_t n, const float* px, float* pw, float* xEst_host,
                     float* PEst_host, double* sum_w_out_host);
 
@@ -181,6 +186,27 @@ int crb_pf_estimate(crb_ctx* ctx, int64_t n, const float* px, float* pw, float* 
 int crb_pf_resample(crb_ctx* ctx, int64_t n, float* px, float* pw, float* px_tmp,
                     const float* uniforms, uint64_t seed, float nth, int* did_resample_host,
                     double* neff_host);
+
+/* One COMPLETE filter iteration without a host round trip: predict + weight (:81-102), normalise + estimate +
+ * covariance (:104-107), Neff (:126) and, DECIDED ON THE DEVICE (:127), low-variance resampling (:128-147).
+ *   px [4][n]      in/out: predicted particles (like crb_pf_predict_weight_batched)
+ *   pw [n]         in/out: normalised weights, or 1/n after a resampling
+ *   px_next [4][n] out: the particles for the next iteration - the resampled set, or a copy of px when
+ *                  Neff >= nth.  Ping-pong px / px_next between calls (no device copy, no decision to read back).
+ *   noise / seed, landmarks, n_lm, prm: as crb_pf_predict_weight_batched; uniforms / resample_seed, nth: as
+ *                  crb_pf_resample
+ *   result_dev [CRB_PF_RESULT_LEN] (device, f64): [0..3] xEst, [4..19] PEst (column-major), [20] sum of the
+ *                  un-normalised weights, [21] Neff, [22] 1.0 if resampled, [23] sum of squared weights
+ * Everything is enqueued on the context's stream (capturable in a CUDA graph).  On a context with a communicator
+ * (a filter sharded over GPUs) the weight sum and the moments are all-reduced (one 120-byte all-reduce), every
+ * rank gets the global xEst / PEst, weights are normalised globally, and particles are NOT resampled (px_next is
+ * a copy; [21..23] are not written).  Also fixes round 1's resampling for n that is not a power of two (the
+ * running maximum of resampleid, see the kernel).
+ * Replaces: pf_localization() + resampling(), src/particle_filter.cpp:73-148. */
+#define CRB_PF_RESULT_LEN 24
+int crb_pf_step(crb_ctx* ctx, int64_t n, float* px, float* pw, float* px_next, const float* noise,
+                uint64_t seed, const float* landmarks, int n_lm, const crb_pf_params* prm,
+                const float* uniforms, uint64_t resample_seed, float nth, double* result_dev);
 
 /* ---- MPC -------------------------------------------------------------------------------------- */
 /* Problem constants: src/model_predictive_control.cpp:23-48 (macros), cost weights :202-210 and

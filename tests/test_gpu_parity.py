@@ -741,3 +741,107 @@ def test_ekf_track_matches_the_multi_step_launch_bitwise(engine, pinned):
         engine.ekf_estimation(xk, Pk, _dev(z[:6])[0], _dev(u[:6])[0], n_steps=3)
         torch.cuda.synchronize()
         assert np.array_equal(outs[2].numpy(), xk.cpu().numpy())
+
+
+# ---- one complete PF iteration on the device (crb_pf_step) ------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [300_001, 1_000_000])
+def test_pf_step_is_the_composition_of_the_reference_stages(engine, n):
+    """predict+weight (:81-102) -> normalise, estimate, covariance (:104-107) -> Neff, resampling (:120-148) in ONE
+    call without a host round trip, against the oracle's stages.  n = 10^6 is not a power of two: j/NP is then
+    inexact in binary32 and adjacent resampleids can be inverted; the reference's monotone search index makes
+    that a running maximum, which the gather kernel reproduces (round 1 did not)."""
+    import torch
+    px, pw, noise = synth.pf_inputs(n)
+    lm = synth.pf_landmarks(8)
+    rng = np.random.default_rng(4)
+    u = (1.0 + rng.random(n)).astype(np.float32)
+    pxo, pwo = O.pf_predict_weight_batched(px, pw, noise, lm)
+    pwn, xeo, Peo, swo = O.pf_estimate(pxo, pwo)
+    # (a) nth = 0: never resample -> px_next is a copy, pw the normalised weights
+    pxd, pwd, nd, ud = _dev(px, pw, noise, u)
+    nxt = torch.empty_like(pxd)
+    res = engine.pf_step(pxd, pwd, nxt, nd, lm, uniforms=ud, nth=0.0)
+    torch.cuda.synchronize()
+    r = res.cpu().numpy()
+    gx, gw = pxd.cpu().numpy(), pwd.cpu().numpy()
+    assert r[22] == 0.0 and np.array_equal(nxt.cpu().numpy(), gx)
+    assert (gx == pxo).all(axis=0).mean() > 1 - 1e-5
+    np.testing.assert_allclose(gw, pwn, rtol=2e-5, atol=1e-30)
+    assert abs(r[20] - swo) <= 1e-5 * abs(swo)
+    np.testing.assert_allclose(r[0:4], xeo, rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(r[4:20].reshape(4, 4).T, Peo, rtol=1e-4, atol=1e-6)
+    neff_o = 1.0 / float(np.float32(np.sum(gw.astype(np.float64) ** 2)))
+    assert abs(r[21] - neff_o) <= 1e-5 * neff_o
+    # (b) nth = n: always resample -> the index work is bit-exact against the oracle run on the GPU's own weights
+    pxd2, pwd2 = _dev(px, pw)
+    nxt2 = torch.empty_like(pxd2)
+    res2 = engine.pf_step(pxd2, pwd2, nxt2, nd, lm, uniforms=ud, nth=float(n))
+    torch.cuda.synchronize()
+    px2, pw2, did_o, _ = O.pf_resample(gx, gw, u.astype(np.float64), nth=float(n))
+    assert res2.cpu().numpy()[22] == 1.0 and did_o
+    assert np.array_equal(nxt2.cpu().numpy(), px2) and np.array_equal(pwd2.cpu().numpy(), pw2)
+    # the stand-alone entry gives the same particles (its cumulative weights are materialised, not fused)
+    pxd3, pwd3 = _dev(gx, gw)
+    engine.pf_resample(pxd3, pwd3, uniforms=ud, nth=float(n))
+    torch.cuda.synchronize()
+    assert np.array_equal(pxd3.cpu().numpy(), px2)
+
+
+def _pf_shard_worker(rank, world, port, n, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from cpprobotics_b200 import Engine, _lib as L
+    eng = Engine(rank)
+    buf = torch.zeros(L.CRB_COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        buf.copy_(torch.frombuffer(bytearray(eng.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(buf, 0)
+    eng.comm_init(world, rank, bytes(buf.cpu().numpy().tobytes()))
+    px, pw, noise = synth.pf_inputs(n)
+    lm = synth.pf_landmarks(8)
+    k = n // world
+    sl = slice(rank * k, (rank + 1) * k)
+    pxd, pwd, nd = (torch.from_numpy(np.ascontiguousarray(a[..., sl])).cuda() for a in (px, pw, noise))
+    # index-addressed noise: shard r applies the noise of particles [r k, (r+1) k)
+    nxt = torch.empty_like(pxd)
+    res = eng.pf_step(pxd, pwd, nxt, nd, lm, nth=0.0)
+    torch.cuda.synchronize()
+    q.put((rank, res.cpu().numpy().copy(), pwd.cpu().numpy().copy()))
+    dist.barrier()
+    eng.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_pf_sharded_over_two_gpus_equals_the_single_gpu_estimate(engine):
+    """SURVEY f-2: pw / pw.sum() (:104) across shards is one small all-reduce inside libcrb; every rank must get the
+    single-GPU estimate and globally normalised weights."""
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    n, world = 400_000, 2
+    px, pw, noise = synth.pf_inputs(n)
+    lm = synth.pf_landmarks(8)
+    pxd, pwd, nd = _dev(px, pw, noise)
+    nxt = torch.empty_like(pxd)
+    want = engine.pf_step(pxd, pwd, nxt, nd, lm, nth=0.0).cpu().numpy()
+    want_w = pwd.cpu().numpy()
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_pf_shard_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=240) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+    for rank, res, w in got:
+        np.testing.assert_allclose(res[0:21], want[0:21], rtol=1e-9, atol=1e-9)   # same sums, other association
+        k = n // world
+        np.testing.assert_allclose(w, want_w[rank * k:(rank + 1) * k], rtol=1e-6, atol=0)
