@@ -33,6 +33,7 @@ struct crb_ctx {
   int mpc_tasks_attr_set;
   int ekf_tma_attr_set;
   int mpc_v0_attr_set;
+  unsigned* tickets;      // 64 zeroed words of device memory: "last block finishes the job" counters (kept at zero)
   // NCCL communicator (crb_comm.cu); NULL = single GPU
   void* comm;
   int comm_world, comm_rank;

@@ -1,0 +1,8 @@
+#!/bin/bash
+OUT=gpurun_out; mkdir -p $OUT
+TAG=${1:-r2h}
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "pf" > $OUT/pytest_$TAG.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_$TAG.log; tail -12 $OUT/pytest_$TAG.log
+timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu --workload pf > $OUT/bench_pf_$TAG.json 2>$OUT/bench_pf_$TAG.err; tail -2 $OUT/bench_pf_$TAG.err
+python scripts/show_bench.py $OUT/bench_pf_$TAG.json | grep "PF"
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:crb_pf -c 60 --csv --log-file $OUT/launches_pf_$TAG.csv python bench.py --steps 4 --warmup 3 --no-cpu --workload pf > /dev/null 2>&1
+python scripts/launch_times.py $OUT/launches_pf_$TAG.csv
