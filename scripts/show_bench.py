@@ -2,7 +2,7 @@
 import json
 import sys
 
-d = json.loads(open(sys.argv[1]).readline())
+d = json.loads([l for l in open(sys.argv[1]) if l.startswith('{')][-1])
 
 
 def g(o, *k):
