@@ -60,6 +60,9 @@ extern "C" int mpc_tasks_sim_solve(int64_t n, int T, const float* x0, const floa
     sl.rec = slab + (size_t)s * N * MPC_REC;
     sl.pol = 0;
     sl.ring = 0;
+    sl.ring_bulk = 0;
+    sl.mbar = 0;
+    sl.rounds[0] = sl.rounds[1] = sl.rounds[2] = 0;
     return sl;
   };
   for (int s = 0; s < S; ++s) mpc_sw_int(slot_of(s), MPC_SW_PROB) = -1;
@@ -105,7 +108,7 @@ extern "C" int mpc_tasks_sim_solve(int64_t n, int T, const float* x0, const floa
     } else {
       for (size_t k = 0; k < take; ++k) {
         MpcSlot sl = slot_of(q[k]);
-        phase[q[k]] = kind == MPC_PH_BW ? mpc_task_bw(sl, T, p) : mpc_task_fw(sl, T, p);
+        phase[q[k]] = kind == MPC_PH_BW ? mpc_task_bw(sl, T, p) : mpc_task_fw<false>(sl, T, p);
       }
     }
   }
