@@ -38,6 +38,7 @@
 struct MpcTaskArgs {
   int64_t count, ld_in, ld_out;
   int T, S, slot_words;
+  int fill_min;                // scheduler: do not start a sweep with fewer slots than this while others are in flight
   const float* x0;
   const float* xref;
   const float* u_init;
@@ -119,6 +120,7 @@ crb_mpc_tasks_kernel(const __grid_constant__ MpcTaskArgs A, const __grid_constan
     __syncthreads();
   }
   bool have_post = false, active = false;
+  int patience = 2;
   int slot = 0, next = MPC_PH_DEAD;
   for (;;) {
     // ---- one critical section per task: publish the finished sweep's slots, take the next batch -------
@@ -157,10 +159,14 @@ crb_mpc_tasks_kernel(const __grid_constant__ MpcTaskArgs A, const __grid_constan
     int kind = MPC_PH_FW, best = c_fw, hk = h2;
     if (c_bw > best) { kind = MPC_PH_BW; best = c_bw; hk = h1; }
     if (c_refill > best) { kind = MPC_PH_REFILL; best = c_refill; hk = h0; }
-    const int taken = best < 32 ? best : 32;
+    // A thin batch costs a whole sweep of the warp's time.  When the fullest queue has fewer than `A.fill_min` slots,
+    // other warps are in flight (their posts will refill the queues) and the patience is not used up, take
+    // nothing now and look again after the next post.
+    int infl = *(volatile int*)&sc->inflight;
+    const bool hold = best > 0 && best < A.fill_min && infl >= 2 && patience > 0;
+    const int taken = hold ? 0 : (best < 32 ? best : 32);
     active = lane < taken;
     slot = active ? *(volatile int*)&sc->q[kind - 1][(hk + lane) & (MPC_TASK_QS - 1)] : 0;
-    int infl = *(volatile int*)&sc->inflight;
     const int seen = *(volatile int*)&sc->seq;
     __syncwarp();
     if (lane == 0 && taken > 0) {
@@ -172,7 +178,8 @@ crb_mpc_tasks_kernel(const __grid_constant__ MpcTaskArgs A, const __grid_constan
     if (lane == 0) atomicExch(&sc->lock, 0);
     have_post = false;
     if (taken == 0) {
-      if (infl == 0) break;  // nothing waits and nobody is working: this CTA is done
+      if (hold) --patience;
+      if (infl == 0 && best == 0) break;  // nothing waits and nobody is working: this CTA is done
       int spins = 0;         // wait for the next post without touching the lock
       while (*(volatile int*)&sc->seq == seen) {
         __nanosleep(400);
@@ -181,6 +188,7 @@ crb_mpc_tasks_kernel(const __grid_constant__ MpcTaskArgs A, const __grid_constan
       if (spins > (1 << 23)) break;
       continue;
     }
+    patience = 2;
     MpcSlot sl;
     sl.tr = smem + (size_t)slot * SW;
     sl.sw = sl.tr + tr_words;
@@ -295,6 +303,15 @@ int crb_mpc_tasks_launch(crb_ctx* ctx, cudaStream_t st, int64_t count, int64_t l
   MpcTaskArgs a;
   a.count = count; a.ld_in = ld; a.ld_out = ld_out;
   a.T = T; a.S = g.S; a.slot_words = mpc_slot_words(T);
+  {
+    static int fill = -1;   // CRB_MPC_FILL (A/B, read once): 0 disables the hold-back
+    if (fill < 0) {
+      const char* e = getenv("CRB_MPC_FILL");
+      fill = e ? atoi(e) : 28;
+      if (fill < 0 || fill > 32) fill = 28;
+    }
+    a.fill_min = fill;
+  }
   static int bulk = -1;   // CRB_MPC_RING=bulk selects the TMA form of the record ring (A/B, read once)
   if (bulk < 0) {
     const char* e = getenv("CRB_MPC_RING");

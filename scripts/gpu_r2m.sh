@@ -1,0 +1,10 @@
+#!/bin/bash
+OUT=gpurun_out; mkdir -p $OUT
+TAG=${1:-r2m}
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k mpc 2>&1 | tail -2
+{
+for f in 0 24 28 32; do CRB_MPC_FILL=$f CRB_MPC_VARIANT=1 MPC_PROBE_CHECK=0 timeout 300 python scripts/mpc_probe.py 65536 1048576 2>&1 | sed "s/^\[/[FILL=$f /"; done
+CRB_MPC_VARIANT=0 MPC_PROBE_CHECK=0 timeout 300 python scripts/mpc_probe.py 65536
+} 2>&1 | tee $OUT/mpc_probe_$TAG.txt
+MPC_PROBE_CHECK=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:crb_mpc_tasks_kernel -s 3 -c 1 -f \
+   -o $OUT/prof_mpc_$TAG python scripts/mpc_probe.py 65536 > $OUT/prof_mpc_$TAG.stdout 2>&1
