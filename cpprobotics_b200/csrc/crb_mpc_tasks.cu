@@ -304,11 +304,13 @@ int crb_mpc_tasks_launch(crb_ctx* ctx, cudaStream_t st, int64_t count, int64_t l
   a.count = count; a.ld_in = ld; a.ld_out = ld_out;
   a.T = T; a.S = g.S; a.slot_words = mpc_slot_words(T);
   {
-    static int fill = -1;   // CRB_MPC_FILL (A/B, read once): 0 disables the hold-back
+    // CRB_MPC_FILL (A/B, read once; default 0 = off).  Measured on B200: holding back batches thinner than 24 / 28 /
+    // 32 slots costs 1 / 2 / 3 % (config 4) - the idle wait is worth more than the fuller warp.
+    static int fill = -1;
     if (fill < 0) {
       const char* e = getenv("CRB_MPC_FILL");
-      fill = e ? atoi(e) : 28;
-      if (fill < 0 || fill > 32) fill = 28;
+      fill = e ? atoi(e) : 0;
+      if (fill < 0 || fill > 32) fill = 0;
     }
     a.fill_min = fill;
   }
