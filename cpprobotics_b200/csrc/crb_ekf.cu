@@ -343,6 +343,7 @@ static int ekf_launch(crb_ctx* ctx, cudaStream_t st, int64_t count, int64_t ld, 
 extern "C" int crb_ekf_step_batched(crb_ctx* ctx, int64_t n, float* x, float* P, const float* z,
                                     const float* u, const crb_ekf_params* prm, int n_steps) {
   CRB_REQUIRE(ctx != nullptr, "ctx is NULL");
+  CRB_DEVICE_GUARD(ctx);   // ctx->device is current for this call, the caller's device is restored after it
   CRB_REQUIRE(n >= 0 && n_steps >= 1, "n < 0 or n_steps < 1");
   CRB_REQUIRE(prm != nullptr, "prm is NULL");
   if (n == 0) return CRB_OK;

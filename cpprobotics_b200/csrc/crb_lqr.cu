@@ -125,6 +125,7 @@ extern "C" int crb_lqr_dlqr_batched(crb_ctx* ctx, int64_t n, int nx, int nu, con
                                     const float* B, const float* Q, const float* R, int maxiter,
                                     float eps, float* K, float* X, int32_t* iters) {
   CRB_REQUIRE(ctx != nullptr, "ctx is NULL");
+  CRB_DEVICE_GUARD(ctx);   // ctx->device is current for this call, the caller's device is restored after it
   CRB_REQUIRE(n >= 0 && maxiter >= 0, "n < 0 or maxiter < 0");
   CRB_REQUIRE((nx == 4 && nu == 1) || (nx == 5 && nu == 2),
               "supported shapes: (nx, nu) = (4, 1) [lqr_steer_control] or (5, 2) [lqr_speed_steer_control]");

@@ -714,6 +714,7 @@ extern "C" int crb_mpc_solve_batched(crb_ctx* ctx, int64_t n, int T, const float
   int rc = mpc_check(ctx, n, T, x0, xref, prm);
   if (rc) return rc;
   if (n == 0) return CRB_OK;
+  CRB_DEVICE_GUARD(ctx);   // ctx->device is current for this call, the caller's device is restored after it
   rc = crb_ctx_mpc_ws_reserve(ctx, mpc_scratch_floats(ctx, T, n) * sizeof(float));
   if (rc) return rc;
   return mpc_launch(ctx, ctx->stream, n, n, T, x0, xref, u_init, (float*)ctx->mpc_ws, n, sol,
@@ -848,6 +849,7 @@ crb_mpc_plant_update_kernel(int64_t n, float* __restrict__ state, const float* _
 extern "C" int crb_mpc_plant_update_batched(crb_ctx* ctx, int64_t n, float* state, const float* u0,
                                             const crb_mpc_params* prm) {
   CRB_REQUIRE(ctx != nullptr, "ctx is NULL");
+  CRB_DEVICE_GUARD(ctx);   // ctx->device is current for this call, the caller's device is restored after it
   CRB_REQUIRE(prm != nullptr, "prm is NULL");
   CRB_REQUIRE(n >= 0, "n < 0");
   CRB_REQUIRE(prm->dt > 0.0f && prm->wb > 0.0f, "dt and wb must be positive");
@@ -903,6 +905,7 @@ extern "C" int crb_mpc_calc_ref_trajectory_batched(crb_ctx* ctx, int64_t n, int 
                                                    int32_t* target_ind, float* xref,
                                                    const crb_mpc_params* prm) {
   CRB_REQUIRE(ctx != nullptr, "ctx is NULL");
+  CRB_DEVICE_GUARD(ctx);   // ctx->device is current for this call, the caller's device is restored after it
   CRB_REQUIRE(n >= 0 && T >= 1 && T <= CRB_MPC_MAX_T, "n < 0 or T out of range");
   CRB_REQUIRE(ncourse >= 1 && dl > 0.0f, "empty course or dl <= 0");
   CRB_REQUIRE(prm != nullptr && prm->dt > 0.0f, "prm is NULL or dt <= 0");

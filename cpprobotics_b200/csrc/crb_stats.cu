@@ -84,6 +84,7 @@ crb_stats_combine_kernel(int64_t n, const double* __restrict__ partial, double* 
 extern "C" int crb_stats_reduce(crb_ctx* ctx, int64_t n, int64_t i0, const float* values,
                                 const int32_t* status, const int32_t* iters, double* stats_dev) {
   CRB_REQUIRE(ctx != nullptr, "ctx is NULL");
+  CRB_DEVICE_GUARD(ctx);   // ctx->device is current for this call, the caller's device is restored after it
   CRB_REQUIRE(n > 0 && values && stats_dev, "n <= 0 or NULL array");
   int rc = crb_ctx_scratch_reserve(ctx, (size_t)ST_BLOCKS * 8 * sizeof(double));
   if (rc) return rc;
