@@ -214,31 +214,58 @@ def comm_setup(eng, rank, world):
     eng.comm_init(world, rank, bytes(buf.cpu().numpy().tobytes()))
 
 
+NUMA_INFO = {}
+
+
+def gpu_numa_cpus(device_index=0):
+    """CPUs of the NUMA node the GPU hangs off (PCI bus id from nvidia-smi -> sysfs numa_node -> cpulist), or None.
+    The result (or the reason it is unknown) is kept in NUMA_INFO and reported in the JSON line."""
+    if device_index in NUMA_INFO:
+        return NUMA_INFO[device_index].get("cpus")
+    info = {"node": None, "cpus": None, "why": None}
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=index,pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        rows = [l.split(",") for l in out.strip().splitlines() if "," in l]
+        phys = device_index
+        if visible:
+            ids = [v.strip() for v in visible.split(",")]
+            if device_index < len(ids) and ids[device_index].isdigit():
+                phys = int(ids[device_index])
+        bus = next((r[1].strip() for r in rows if int(r[0]) == phys), None)
+        if bus is None:
+            raise RuntimeError("GPU not listed by nvidia-smi")
+        dom, rest = bus.split(":", 1)
+        path = f"/sys/bus/pci/devices/{dom[-4:].lower()}:{rest.lower()}/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            raise RuntimeError("numa_node = -1 (single node or not exposed)")
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        info.update(node=node, cpus=cpus)
+    except Exception as exc:
+        info["why"] = str(exc)[:120]
+    NUMA_INFO[device_index] = info
+    return info["cpus"]
+
+
 def numa_pinned(a, device_index=0):
-    """Pinned host copy of `a` allocated while this thread runs on the CPUs of the GPU's NUMA node, so that the
-    pages are first-touched there (eight GPUs pulling from one node's DRAM was r1's e2e limiter at N = 8)."""
+    """Pinned host copy of `a` allocated (and first touched) while this thread runs on the CPUs of the GPU's NUMA
+    node (eight GPUs pulling from one node's DRAM was r1's e2e limiter at N = 8)."""
     import torch
     old = None
+    cpus = gpu_numa_cpus(device_index)
     try:
-        node = None
-        bus = torch.cuda.get_device_properties(device_index).pci_bus_id if hasattr(
-            torch.cuda.get_device_properties(device_index), "pci_bus_id") else None
-        if bus is not None:
-            dom = torch.cuda.get_device_properties(device_index).pci_domain_id
-            devid = torch.cuda.get_device_properties(device_index).pci_device_id
-            path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{devid:02x}.0/numa_node"
-            if os.path.exists(path):
-                node = int(open(path).read().strip())
-        if node is not None and node >= 0:
-            cl = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
-            cpus = set()
-            for part in cl.split(","):
-                lo, _, hi = part.partition("-")
-                cpus.update(range(int(lo), int(hi or lo) + 1))
+        if cpus:
             old = os.sched_getaffinity(0)
             use = cpus & old
             if use:
                 os.sched_setaffinity(0, use)
+            else:
+                old = None
     except Exception:
         old = None
     try:
@@ -250,14 +277,6 @@ def numa_pinned(a, device_index=0):
     return t
 
 
-def pinned(a):
-    import torch
-    return numa_pinned(np.ascontiguousarray(a), torch.cuda.current_device())
-
-
-# =========================================================================================================
-# workloads: each returns a dict with value / ms_per_step / roofline / e2e / cpu_baseline pieces
-# =========================================================================================================
 REPLAYS = 10
 LAST_TIMING = {}
 
@@ -1052,6 +1071,8 @@ def run_ours(args):
         cfg["pf_workload"] = res["pf"]["config"]["workload"] + " (BASELINE.json configs[2])"
     if TRAFFIC_STALE:
         cfg["traffic_stale"] = sorted(set(TRAFFIC_STALE))
+    ni = NUMA_INFO.get(local, {})
+    cfg["host_buffers_numa"] = {"node_of_gpu": ni.get("node"), "unknown_because": ni.get("why")}
     if res:
         line["extra"] = res
     if rank == 0:
