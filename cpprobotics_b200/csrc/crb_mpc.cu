@@ -609,12 +609,12 @@ static size_t mpc_scratch_floats(crb_ctx* ctx, int T, int64_t count) {
 static int mpc_launch(crb_ctx* ctx, cudaStream_t st, int64_t count, int64_t ld, int T,
                       const float* x0, const float* xref, const float* u_init, float* scratch,
                       int64_t ld_out, float* sol, float* u0, float* cost, int32_t* status,
-                      int32_t* iters, const crb_mpc_params* prm) {
+                      int32_t* iters, const crb_mpc_params* prm, const int32_t* hint = nullptr) {
   MpcP p;
   mpc_fill(&p, prm);
   if (mpc_variant() == 1)
     return crb_mpc_tasks_launch(ctx, st, count, ld, T, x0, xref, u_init, scratch, ld_out, sol, u0, cost,
-                                status, iters, p);
+                                status, iters, p, hint);
   // Experiment kept for A/B (CRB_MPC_L2=1): an L2 persisting access-policy window over the solver
   // workspace.  Measured on B200: 36.1 M solves/s with it vs 60.0 M without (the set-aside shrinks the
   // normal L2 and the 152 MB workspace thrashes it), so it is OFF by default.
@@ -719,6 +719,26 @@ extern "C" int crb_mpc_solve_batched(crb_ctx* ctx, int64_t n, int T, const float
   if (rc) return rc;
   return mpc_launch(ctx, ctx->stream, n, n, T, x0, xref, u_init, (float*)ctx->mpc_ws, n, sol,
                     u0, cost, status, iters, prm);
+}
+
+// The same solve with a scheduling hint per problem (device, [n]): an estimate of its work, e.g. the `iters` the
+// previous solve of the same agent returned (receding-horizon MPC calls the solver every control step,
+// src/model_predictive_control.cpp:372-378).  Problems with the largest hints start first, which removes most of the
+// tail in which a few late-started long problems run alone.  Results are bit-identical to
+// crb_mpc_solve_batched; hint must not alias `iters` (it is read while results are written).
+extern "C" int crb_mpc_solve_batched_hinted(crb_ctx* ctx, int64_t n, int T, const float* x0, const float* xref,
+                                            const float* u_init, const crb_mpc_params* prm, float* sol,
+                                            float* u0, float* cost, int32_t* status, int32_t* iters,
+                                            const int32_t* hint) {
+  int rc = mpc_check(ctx, n, T, x0, xref, prm);
+  if (rc) return rc;
+  CRB_REQUIRE(hint == nullptr || hint != iters, "hint must not alias iters");
+  if (n == 0) return CRB_OK;
+  CRB_DEVICE_GUARD(ctx);
+  rc = crb_ctx_mpc_ws_reserve(ctx, mpc_scratch_floats(ctx, T, n) * sizeof(float));
+  if (rc) return rc;
+  return mpc_launch(ctx, ctx->stream, n, n, T, x0, xref, u_init, (float*)ctx->mpc_ws, n, sol, u0, cost, status,
+                    iters, prm, hint);
 }
 
 extern "C" int crb_mpc_solve_batched_host(crb_ctx* ctx, int64_t n, int T, const float* x0,

@@ -42,7 +42,8 @@ struct MpcTaskArgs {
   const float* x0;
   const float* xref;
   const float* u_init;
-  unsigned long long* header;  // [0] next problem index, [1] error word
+  unsigned long long* header;  // [0] next problem index, [1] error word; bytes 256..511: histogram of the hints
+  const int32_t* hint;         // optional scheduling hints (NULL: index order), see mpc_hint_thresholds
   float* slab;                 // [grid][S][T-1][MPC_REC]
   float* sol;
   float* u0;
@@ -59,6 +60,7 @@ struct alignas(16) MpcSched {  // 16-byte multiple: the cp.async rings follow it
   int inflight;           // warps that are executing a task
   int lock;
   int seq;                // bumped whenever work is posted: idle warps watch it instead of the lock
+  int hthr[4];            // hinted order: bucket thresholds (3 used)
 };
 static_assert(sizeof(MpcSched) % 16 == 0, "record rings must start 16-byte aligned");
 
@@ -89,6 +91,9 @@ crb_mpc_tasks_kernel(const __grid_constant__ MpcTaskArgs A, const __grid_constan
     sc->head[0] = sc->head[1] = sc->head[2] = 0;
     sc->tail[0] = S; sc->tail[1] = sc->tail[2] = 0;
     sc->inflight = 0; sc->lock = 0; sc->seq = 0;
+    sc->hthr[0] = sc->hthr[1] = sc->hthr[2] = sc->hthr[3] = 0;
+    if (A.hint != nullptr)   // the same thresholds in every CTA: the histogram is complete before this kernel starts
+      mpc_hint_thresholds(reinterpret_cast<const unsigned*>(A.header) + 64, A.count, sc->hthr);
   }
   __syncthreads();
   float* const slab = A.slab + (size_t)blockIdx.x * S * N * MPC_REC;
@@ -216,10 +221,42 @@ crb_mpc_tasks_kernel(const __grid_constant__ MpcTaskArgs A, const __grid_constan
       // lanes, so the loads of a refill are coalesced rows of x0 / xref
       if (active && mpc_sw_int(sl, MPC_SW_PROB) >= 0)
         mpc_task_retire(sl, T, p, A.ld_out, A.sol, A.u0, A.cost, A.status, A.iters);
-      unsigned long long base = 0;
-      if (lane == 0) base = atomicAdd(&A.header[0], (unsigned long long)taken);
-      base = __shfl_sync(FULL, base, 0);
-      const int64_t i = (int64_t)base + lane;
+      int64_t i;
+      if (A.hint == nullptr) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&A.header[0], (unsigned long long)taken);
+        base = __shfl_sync(FULL, base, 0);
+        i = (int64_t)base + lane;
+      } else {
+        // hinted order: the counter runs over MPC_HINT_PASSES copies of the index space; candidate v is problem
+        // v mod count, taken in pass v / count iff that is its bucket.  Every candidate is claimed by exactly one
+        // lane and every problem matches in exactly one pass, so each problem is solved once; a lane without a
+        // match claims again.  Each round moves the global counter, so the loop ends after at most
+        // MPC_HINT_PASSES * count candidates over the whole grid.
+        const unsigned long long cnt = (unsigned long long)A.count;
+        const int t0 = sc->hthr[0], t1 = sc->hthr[1], t2 = sc->hthr[2];
+        bool need = active;
+        i = A.count;   // "exhausted" unless a candidate matches
+        for (;;) {
+          const unsigned m = __ballot_sync(FULL, need);
+          if (m == 0u) break;
+          unsigned long long base = 0;
+          if (lane == 0) base = atomicAdd(&A.header[0], (unsigned long long)__popc(m));
+          base = __shfl_sync(FULL, base, 0);
+          if (need) {
+            const unsigned long long v = base + (unsigned long long)__popc(m & lanemask_lt());
+            const int pass = (int)(v >= cnt) + (int)(v >= 2ull * cnt) + (int)(v >= 3ull * cnt);
+            if (v >= (unsigned long long)MPC_HINT_PASSES * cnt) {
+              need = false;   // every pass is exhausted
+            } else {
+              const int64_t c = (int64_t)(v - (unsigned long long)pass * cnt);
+              const int h = mpc_hint_clamp(__ldg(A.hint + c));
+              const int b = h >= t0 ? 0 : (h >= t1 ? 1 : (h >= t2 ? 2 : 3));
+              if (b == pass) { i = c; need = false; }
+            }
+          }
+        }
+      }
       if (active) {
         if (i < A.count) {
           next = mpc_task_init(sl, T, p, i, A.ld_in, A.x0, A.xref, A.u_init);
@@ -232,6 +269,18 @@ crb_mpc_tasks_kernel(const __grid_constant__ MpcTaskArgs A, const __grid_constan
     __threadfence_block();  // the sweep's results are visible before the slots are queued again
     have_post = true;
   }
+}
+
+// histogram of the clamped hints (64 bins, zeroed by the launcher) for mpc_hint_thresholds
+__global__ void __launch_bounds__(256) crb_mpc_hint_hist_kernel(int64_t count, const int32_t* __restrict__ hint,
+                                                                unsigned* __restrict__ hist) {
+  __shared__ unsigned sh[MPC_HINT_BINS];
+  if (threadIdx.x < MPC_HINT_BINS) sh[threadIdx.x] = 0u;
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+    atomicAdd(&sh[mpc_hint_clamp(hint[i])], 1u);
+  __syncthreads();
+  if (threadIdx.x < MPC_HINT_BINS && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
 }
 
 // Launch geometry for `count` problems of horizon T: warps per CTA, slots per CTA, CTAs, shared memory.
@@ -275,17 +324,17 @@ static bool mpc_tasks_geometry(int sm_count, int T, int64_t count, MpcTaskGeom* 
   return true;
 }
 
-// header (256 B) + slab of stage records + 256 B of alignment slack
+// header (512 B: counters + hint histogram) + slab of stage records + 256 B of alignment slack
 size_t crb_mpc_tasks_scratch_bytes(int sm_count, int T, int64_t count) {
   MpcTaskGeom g;
-  if (!mpc_tasks_geometry(sm_count, T, count, &g)) return 512;
-  return 512 + (size_t)g.grid * g.S * (size_t)(T - 1) * MPC_REC * sizeof(float);
+  if (!mpc_tasks_geometry(sm_count, T, count, &g)) return 768;
+  return 768 + (size_t)g.grid * g.S * (size_t)(T - 1) * MPC_REC * sizeof(float);
 }
 
 int crb_mpc_tasks_launch(crb_ctx* ctx, cudaStream_t st, int64_t count, int64_t ld, int T,
                          const float* x0, const float* xref, const float* u_init, void* scratch,
                          int64_t ld_out, float* sol, float* u0, float* cost, int32_t* status,
-                         int32_t* iters, const MpcP& p) {
+                         int32_t* iters, const MpcP& p, const int32_t* hint) {
   CRB_REQUIRE(count < ((int64_t)1 << 31), "more than 2^31 problems in one launch");
   MpcTaskGeom g;
   if (!mpc_tasks_geometry(ctx->sm_count, T, count, &g)) {
@@ -321,9 +370,16 @@ int crb_mpc_tasks_launch(crb_ctx* ctx, cudaStream_t st, int64_t count, int64_t l
   }
   a.x0 = x0; a.xref = xref; a.u_init = u_init;
   a.header = (unsigned long long*)base;
-  a.slab = (float*)(base + 256);
+  a.slab = (float*)(base + 512);
   a.sol = sol; a.u0 = u0; a.cost = cost; a.status = status; a.iters = iters;
-  CRB_CUDA(cudaMemsetAsync(base, 0, 256, st));
+  a.hint = hint;
+  CRB_CUDA(cudaMemsetAsync(base, 0, 512, st));
+  if (hint != nullptr) {
+    int hg = (int)((count + 2047) / 2048);
+    if (hg > 4 * ctx->sm_count) hg = 4 * ctx->sm_count;
+    crb_mpc_hint_hist_kernel<<<hg < 1 ? 1 : hg, 256, 0, st>>>(count, hint, (unsigned*)(base + 256));
+    ctx->launches++;
+  }
   if (bulk)
     crb_mpc_tasks_kernel<true><<<(unsigned)g.grid, g.nwarps * 32, g.smem, st>>>(a, p);
   else

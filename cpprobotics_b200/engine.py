@@ -235,7 +235,7 @@ class Engine:
         return result
 
     # ---- MPC --------------------------------------------------------------------------------------
-    def _mpc(self, fn, dev, x0, xref, T, params, u_init, sol, u0, cost, status, iters):
+    def _mpc(self, fn, dev, x0, xref, T, params, u_init, sol, u0, cost, status, iters, hint=None):
         n = int(x0.shape[-1])
         _shape(x0, 4, n, "x0"); _shape(xref, 4 * T, n, "xref")
         nu = 2 * (T - 1)
@@ -253,7 +253,9 @@ class Engine:
                  _ptr(u0, np.float32, device=dev, name="u0"),
                  _ptr(cost, np.float32, device=dev, name="cost"),
                  _ptr(status, np.int32, device=dev, name="status"),
-                 _ptr(iters, np.int32, device=dev, name="iters")), "crb_mpc_solve_batched")
+                 _ptr(iters, np.int32, device=dev, name="iters"),
+                 *(() if hint is None else (_ptr(hint, np.int32, device=dev, name="hint"),))),
+              "crb_mpc_solve_batched")
 
     def mpc_solve(self, x0, xref, T: int, params: Optional[MpcParams] = None, u_init=None, sol=None,
                   u0=None, cost=None, status=None, iters=None):
@@ -261,6 +263,15 @@ class Engine:
         cost [n], status [n] int32, iters [n] int32 (pre-allocated CUDA tensors or None)."""
         self._mpc(self.lib.crb_mpc_solve_batched, True, x0, xref, T, params, u_init, sol, u0, cost,
                   status, iters)
+
+    def mpc_solve_hinted(self, x0, xref, T: int, hint, params: Optional[MpcParams] = None, u_init=None,
+                         sol=None, u0=None, cost=None, status=None, iters=None):
+        """mpc_solve with a scheduling hint per problem (int32 [n] CUDA tensor, e.g. the previous solve's `iters`):
+        problems with the largest hints start first; the results are bit-identical to mpc_solve."""
+        if int(hint.shape[-1]) != int(x0.shape[-1]):
+            raise ValueError("hint must have one entry per problem")
+        self._mpc(self.lib.crb_mpc_solve_batched_hinted, True, x0, xref, T, params, u_init, sol, u0, cost,
+                  status, iters, hint=hint)
 
     def mpc_solve_host(self, x0, xref, T: int, params: Optional[MpcParams] = None, u_init=None,
                        sol=None, u0=None, cost=None, status=None, iters=None):

@@ -256,6 +256,15 @@ int crb_mpc_solve_batched(crb_ctx* ctx, int64_t n, int T, const float* x0, const
 int crb_mpc_solve_batched_host(crb_ctx* ctx, int64_t n, int T, const float* x0, const float* xref,
                                const float* u_init, const crb_mpc_params* prm, float* sol,
                                float* u0, float* cost, int32_t* status, int32_t* iters);
+/* crb_mpc_solve_batched with a scheduling hint per problem: hint [n] (device, int32, may be NULL) is an estimate
+ * of the problem's work - in a receding-horizon loop (the caller's loop, :372-378, solves the same vehicle every
+ * control step) the `iters` of the agent's previous solve.  The solver is adaptive (3..21 outer iterations on the bench
+ * batch); starting the problems with the largest hints first removes most of the tail in which a few late-started
+ * long problems run alone.  The hint changes the ORDER in which problems start and nothing else: results are
+ * bit-identical to crb_mpc_solve_batched for any hint.  hint must not alias iters. */
+int crb_mpc_solve_batched_hinted(crb_ctx* ctx, int64_t n, int T, const float* x0, const float* xref,
+                                 const float* u_init, const crb_mpc_params* prm, float* sol, float* u0,
+                                 float* cost, int32_t* status, int32_t* iters, const int32_t* hint);
 /* Plant step on the first control: state [4][n] in/out, u0 [2][n] = (a, delta).
  * Uses prm->max_steer, dt, wb, max_speed, min_speed (required, not NULL).  The reference evaluates this
  * step in double because its constants are double macros (:26-38): a parameter equal to the reference's

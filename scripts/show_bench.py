@@ -18,7 +18,10 @@ print("MPC", d["config"].get("mpc_solves_per_s"), "kernel-only", g(d, "roofline"
       "frac", g(d, "roofline", "mpc", "frac"), "peak", g(d, "roofline", "mpc", "peak"), "traffic", g(d, "roofline", "mpc", "traffic"))
 print("MPC e2e", g(d, "e2e", "mpc", "value"), "cpu", g(d, "cpu_baseline", "mpc", "value"), "acc",
       d["config"].get("mpc_accuracy_vs_float64_optimum"))
+print("MPC hinted", g(d, "roofline", "mpc", "receding_horizon"))
 print("MPC config5", d["config"].get("mpc_config5"))
+print("MPC config5 hinted", g(d, "roofline", "mpc_config5", "receding_horizon"))
+print("NUMA", d["config"].get("host_buffers_numa"))
 print("PF", d["config"].get("pf_particles_per_s"), "frac", g(d, "roofline", "pf", "frac"), "full iter ms",
       g(d, "extra", "pf_full_iteration", "ms_per_step"))
 print("cpu ekf", g(d, "cpu_baseline", "value"), g(d, "cpu_baseline", "cores"), g(d, "cpu_baseline", "spread"),

@@ -33,9 +33,14 @@ static uint64_t rng_next(uint64_t* s) {
   return z ^ (z >> 31);
 }
 
+extern "C" void mpc_tasks_sim_hint_thresholds(const unsigned* hist, int64_t n, int* thr) {
+  mpc_hint_thresholds(hist, n, thr);
+}
+
 extern "C" int mpc_tasks_sim_solve(int64_t n, int T, const float* x0, const float* xref, const float* u_init,
                                    const sim_params* prm, float* sol, float* u0, float* cost, int32_t* status,
-                                   int32_t* iters, int S, uint64_t seed, int64_t* task_counts /*[3] or NULL*/) {
+                                   int32_t* iters, int S, uint64_t seed, int64_t* task_counts /*[3] or NULL*/,
+                                   const int32_t* hint /*[n] or NULL: the kernel's hinted order*/) {
   MpcP p;
   p.dt = prm->dt;
   p.inv_dt = 1.0f / prm->dt;
@@ -66,8 +71,14 @@ extern "C" int mpc_tasks_sim_solve(int64_t n, int T, const float* x0, const floa
     return sl;
   };
   for (int s = 0; s < S; ++s) mpc_sw_int(slot_of(s), MPC_SW_PROB) = -1;
-  int64_t next_problem = 0;
+  int64_t next_problem = 0;   // the kernel's global counter (virtual candidates when hints are given)
   int64_t counts[3] = {0, 0, 0};
+  int hthr[MPC_HINT_PASSES - 1] = {0, 0, 0};
+  if (hint) {
+    unsigned hist[MPC_HINT_BINS] = {0};
+    for (int64_t i = 0; i < n; ++i) hist[mpc_hint_clamp(hint[i])] += 1u;
+    mpc_hint_thresholds(hist, n, hthr);
+  }
   uint64_t rs = seed;
   for (;;) {
     // waiting slots by kind
@@ -93,11 +104,36 @@ extern "C" int mpc_tasks_sim_solve(int64_t n, int T, const float* x0, const floa
         MpcSlot sl = slot_of(q[k]);
         if (mpc_sw_int(sl, MPC_SW_PROB) >= 0) mpc_task_retire(sl, T, p, n, sol, u0, cost, status, iters);
       }
-      const int64_t base = next_problem;
-      next_problem += (int64_t)take;
+      // problem indices of the lanes: consecutive ones, or (hinted order) the kernel's claim loop - every round the
+      // lanes that still need a problem claim one candidate each; candidate v is problem v mod n in pass v / n
+      std::vector<int64_t> pick(take, n);
+      if (!hint) {
+        for (size_t k = 0; k < take; ++k) pick[k] = next_problem + (int64_t)k;
+        next_problem += (int64_t)take;
+      } else {
+        std::vector<char> need(take, 1);
+        for (;;) {
+          int64_t cnt = 0;
+          for (size_t k = 0; k < take; ++k) cnt += need[k];
+          if (cnt == 0) break;
+          int64_t v = next_problem;
+          next_problem += cnt;
+          for (size_t k = 0; k < take; ++k) {
+            if (!need[k]) continue;
+            if (v >= (int64_t)MPC_HINT_PASSES * n) {
+              need[k] = 0;
+            } else {
+              const int pass = (int)(v / n);
+              const int64_t c = v - (int64_t)pass * n;
+              if (mpc_hint_bucket(hint[c], hthr) == pass) { pick[k] = c; need[k] = 0; }
+            }
+            ++v;
+          }
+        }
+      }
       for (size_t k = 0; k < take; ++k) {
         MpcSlot sl = slot_of(q[k]);
-        const int64_t i = base + (int64_t)k;
+        const int64_t i = pick[k];
         if (i < n) {
           phase[q[k]] = mpc_task_init(sl, T, p, i, n, x0, xref, u_init);
         } else {

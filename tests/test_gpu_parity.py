@@ -628,6 +628,37 @@ def test_full_size_mpc_65536_bit_exact_vs_oracle(engine):
     assert (got["status"] == 0).mean() > 0.999
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,kind", [(65536, "iters"), (65536, "random"), (5000, "constant"), (40_000, "one_long"),
+                                    (70_001, "negative_and_huge")])
+def test_mpc_hinted_order_gives_the_same_bits(engine, n, kind):
+    """crb_mpc_solve_batched_hinted changes the order in which problems start (largest hints first, four passes over
+    the index space) and nothing else: every output word equals the un-hinted solve for any hint array, including
+    useless ones.  Outputs are pre-filled with a pattern, so a skipped problem would show."""
+    import torch
+    T = 20
+    st, xref = _mpc_case(n, T)
+    prm = _params()
+    want = _mpc_gpu(engine, st, xref, T, prm)
+    rng = np.random.default_rng(3)
+    hint = {"iters": want["iters"], "random": rng.integers(0, 40, n), "constant": np.full(n, 7),
+            "one_long": np.where(np.arange(n) == n // 2, 50, 3),
+            "negative_and_huge": rng.integers(-5, 10_000, n)}[kind].astype(np.int32)
+    std, xrd, hd = _dev(st, xref, hint)
+    nsol = 4 * T + 2 * (T - 1)
+    out = dict(sol=torch.full((nsol, n), float("nan"), dtype=torch.float32, device="cuda"),
+               u0=torch.full((2, n), float("nan"), dtype=torch.float32, device="cuda"),
+               cost=torch.full((n,), float("nan"), dtype=torch.float32, device="cuda"),
+               status=torch.full((n,), -7, dtype=torch.int32, device="cuda"),
+               iters=torch.full((n,), -7, dtype=torch.int32, device="cuda"))
+    engine.mpc_solve_hinted(std, xrd, T, hd, prm, **out)
+    torch.cuda.synchronize()
+    for k in ("status", "iters", "u0", "cost", "sol"):
+        assert np.array_equal(out[k].cpu().numpy(), want[k], equal_nan=True), k
+    with pytest.raises(Exception):     # the hint is read while iters is written: aliasing is refused
+        engine.mpc_solve_hinted(std, xrd, T, out["iters"], prm, iters=out["iters"])
+
+
 def test_full_size_resample_properties_2pow20(engine):
     """Size-independent properties of resampling() at 2^20 particles (no oracle needed): the surviving source
     indices are non-decreasing in j (both resampleid and the cumulative weights are monotone), every output
