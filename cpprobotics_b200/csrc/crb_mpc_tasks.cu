@@ -61,6 +61,7 @@ struct alignas(16) MpcSched {  // 16-byte multiple: the cp.async rings follow it
   int lock;
   int seq;                // bumped whenever work is posted: idle warps watch it instead of the lock
   int hthr[4];            // hinted order: bucket thresholds (3 used)
+  int hempty[4];          // hinted order: 1 = no problem falls into this bucket (its pass is skipped at once)
 };
 static_assert(sizeof(MpcSched) % 16 == 0, "record rings must start 16-byte aligned");
 
@@ -92,8 +93,12 @@ crb_mpc_tasks_kernel(const __grid_constant__ MpcTaskArgs A, const __grid_constan
     sc->tail[0] = S; sc->tail[1] = sc->tail[2] = 0;
     sc->inflight = 0; sc->lock = 0; sc->seq = 0;
     sc->hthr[0] = sc->hthr[1] = sc->hthr[2] = sc->hthr[3] = 0;
-    if (A.hint != nullptr)   // the same thresholds in every CTA: the histogram is complete before this kernel starts
-      mpc_hint_thresholds(reinterpret_cast<const unsigned*>(A.header) + 64, A.count, sc->hthr);
+    sc->hempty[0] = sc->hempty[1] = sc->hempty[2] = sc->hempty[3] = 0;
+    if (A.hint != nullptr) {   // the same thresholds in every CTA: the histogram is complete before this kernel starts
+      const unsigned* hist = reinterpret_cast<const unsigned*>(A.header) + 64;
+      mpc_hint_thresholds(hist, A.count, sc->hthr);
+      mpc_hint_empty(hist, sc->hthr, sc->hempty);
+    }
   }
   __syncthreads();
   float* const slab = A.slab + (size_t)blockIdx.x * S * N * MPC_REC;
@@ -248,6 +253,9 @@ crb_mpc_tasks_kernel(const __grid_constant__ MpcTaskArgs A, const __grid_constan
             const int pass = (int)(v >= cnt) + (int)(v >= 2ull * cnt) + (int)(v >= 3ull * cnt);
             if (v >= (unsigned long long)MPC_HINT_PASSES * cnt) {
               need = false;   // every pass is exhausted
+            } else if (sc->hempty[pass]) {
+              // nothing falls into this bucket: move the counter to the end of the pass (its candidates match nothing)
+              atomicMax(&A.header[0], (unsigned long long)(pass + 1) * cnt);
             } else {
               const int64_t c = (int64_t)(v - (unsigned long long)pass * cnt);
               const int h = mpc_hint_clamp(__ldg(A.hint + c));

@@ -74,10 +74,12 @@ extern "C" int mpc_tasks_sim_solve(int64_t n, int T, const float* x0, const floa
   int64_t next_problem = 0;   // the kernel's global counter (virtual candidates when hints are given)
   int64_t counts[3] = {0, 0, 0};
   int hthr[MPC_HINT_PASSES - 1] = {0, 0, 0};
+  int hempty[MPC_HINT_PASSES] = {0, 0, 0, 0};
   if (hint) {
     unsigned hist[MPC_HINT_BINS] = {0};
     for (int64_t i = 0; i < n; ++i) hist[mpc_hint_clamp(hint[i])] += 1u;
     mpc_hint_thresholds(hist, n, hthr);
+    mpc_hint_empty(hist, hthr, hempty);
   }
   uint64_t rs = seed;
   for (;;) {
@@ -125,7 +127,12 @@ extern "C" int mpc_tasks_sim_solve(int64_t n, int T, const float* x0, const floa
             } else {
               const int pass = (int)(v / n);
               const int64_t c = v - (int64_t)pass * n;
-              if (mpc_hint_bucket(hint[c], hthr) == pass) { pick[k] = c; need[k] = 0; }
+              if (hempty[pass]) {   // the kernel's atomicMax: the counter jumps to the end of an empty pass
+                if (next_problem < (int64_t)(pass + 1) * n) next_problem = (int64_t)(pass + 1) * n;
+              } else if (mpc_hint_bucket(hint[c], hthr) == pass) {
+                pick[k] = c;
+                need[k] = 0;
+              }
             }
             ++v;
           }
