@@ -277,6 +277,14 @@ def numa_pinned(a, device_index=0):
     return t
 
 
+def pinned(a):
+    import torch
+    return numa_pinned(np.ascontiguousarray(a), torch.cuda.current_device())
+
+
+# =========================================================================================================
+# workloads: each returns a dict with value / ms_per_step / roofline / e2e / cpu_baseline pieces
+# =========================================================================================================
 REPLAYS = 10
 LAST_TIMING = {}
 

@@ -1,7 +1,7 @@
 #!/bin/bash
 # PF four-launch iteration and MPC hinted order: parity subset + A/B timings.
 OUT=gpurun_out; mkdir -p $OUT
-timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "pf_step or hinted or pf_sharded or resample" > $OUT/o_pytest.log 2>&1; echo "pytest rc=$?" >> $OUT/o_pytest.log
+[ -n "$SKIP_PYTEST" ] || timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "pf_step or hinted or pf_sharded or resample" > $OUT/o_pytest.log 2>&1; echo "pytest rc=$?" >> $OUT/o_pytest.log
 CRB_PF_STEP=1 timeout 300 python bench.py --workload pf --no-cpu --steps 20 --warmup 5 > $OUT/o_pf1.json 2> $OUT/o_pf1.err
 CRB_PF_STEP=2 timeout 300 python bench.py --workload pf --no-cpu --steps 20 --warmup 5 > $OUT/o_pf2.json 2> $OUT/o_pf2.err
 CRB_PF_STEP=2 CRB_PDL=0 timeout 300 python bench.py --workload pf --no-cpu --steps 20 --warmup 5 > $OUT/o_pf2_nopdl.json 2> $OUT/o_pf2_nopdl.err
