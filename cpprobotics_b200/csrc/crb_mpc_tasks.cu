@@ -42,8 +42,8 @@ struct MpcTaskArgs {
   const float* x0;
   const float* xref;
   const float* u_init;
-  unsigned long long* header;  // [0] next problem index, [1] error word; bytes 256..511: histogram of the hints
-  const int32_t* hint;         // optional scheduling hints (NULL: index order), see mpc_hint_thresholds
+  unsigned long long* header;  // [0] next problem index, [1] error word
+  const int32_t* perm;         // hinted order: the k-th problem to start is perm[k] (NULL: index order)
   float* slab;                 // [grid][S][T-1][MPC_REC]
   float* sol;
   float* u0;
@@ -60,8 +60,6 @@ struct alignas(16) MpcSched {  // 16-byte multiple: the cp.async rings follow it
   int inflight;           // warps that are executing a task
   int lock;
   int seq;                // bumped whenever work is posted: idle warps watch it instead of the lock
-  int hthr[4];            // hinted order: bucket thresholds (3 used)
-  int hempty[4];          // hinted order: 1 = no problem falls into this bucket (its pass is skipped at once)
 };
 static_assert(sizeof(MpcSched) % 16 == 0, "record rings must start 16-byte aligned");
 
@@ -92,13 +90,6 @@ crb_mpc_tasks_kernel(const __grid_constant__ MpcTaskArgs A, const __grid_constan
     sc->head[0] = sc->head[1] = sc->head[2] = 0;
     sc->tail[0] = S; sc->tail[1] = sc->tail[2] = 0;
     sc->inflight = 0; sc->lock = 0; sc->seq = 0;
-    sc->hthr[0] = sc->hthr[1] = sc->hthr[2] = sc->hthr[3] = 0;
-    sc->hempty[0] = sc->hempty[1] = sc->hempty[2] = sc->hempty[3] = 0;
-    if (A.hint != nullptr) {   // the same thresholds in every CTA: the histogram is complete before this kernel starts
-      const unsigned* hist = reinterpret_cast<const unsigned*>(A.header) + 64;
-      mpc_hint_thresholds(hist, A.count, sc->hthr);
-      mpc_hint_empty(hist, sc->hthr, sc->hempty);
-    }
   }
   __syncthreads();
   float* const slab = A.slab + (size_t)blockIdx.x * S * N * MPC_REC;
@@ -226,45 +217,12 @@ crb_mpc_tasks_kernel(const __grid_constant__ MpcTaskArgs A, const __grid_constan
       // lanes, so the loads of a refill are coalesced rows of x0 / xref
       if (active && mpc_sw_int(sl, MPC_SW_PROB) >= 0)
         mpc_task_retire(sl, T, p, A.ld_out, A.sol, A.u0, A.cost, A.status, A.iters);
-      int64_t i;
-      if (A.hint == nullptr) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(&A.header[0], (unsigned long long)taken);
-        base = __shfl_sync(FULL, base, 0);
-        i = (int64_t)base + lane;
-      } else {
-        // hinted order: the counter runs over MPC_HINT_PASSES copies of the index space; candidate v is problem
-        // v mod count, taken in pass v / count iff that is its bucket.  Every candidate is claimed by exactly one
-        // lane and every problem matches in exactly one pass, so each problem is solved once; a lane without a
-        // match claims again.  Each round moves the global counter, so the loop ends after at most
-        // MPC_HINT_PASSES * count candidates over the whole grid.
-        const unsigned long long cnt = (unsigned long long)A.count;
-        const int t0 = sc->hthr[0], t1 = sc->hthr[1], t2 = sc->hthr[2];
-        bool need = active;
-        i = A.count;   // "exhausted" unless a candidate matches
-        for (;;) {
-          const unsigned m = __ballot_sync(FULL, need);
-          if (m == 0u) break;
-          unsigned long long base = 0;
-          if (lane == 0) base = atomicAdd(&A.header[0], (unsigned long long)__popc(m));
-          base = __shfl_sync(FULL, base, 0);
-          if (need) {
-            const unsigned long long v = base + (unsigned long long)__popc(m & lanemask_lt());
-            const int pass = (int)(v >= cnt) + (int)(v >= 2ull * cnt) + (int)(v >= 3ull * cnt);
-            if (v >= (unsigned long long)MPC_HINT_PASSES * cnt) {
-              need = false;   // every pass is exhausted
-            } else if (sc->hempty[pass]) {
-              // nothing falls into this bucket: move the counter to the end of the pass (its candidates match nothing)
-              atomicMax(&A.header[0], (unsigned long long)(pass + 1) * cnt);
-            } else {
-              const int64_t c = (int64_t)(v - (unsigned long long)pass * cnt);
-              const int h = mpc_hint_clamp(__ldg(A.hint + c));
-              const int b = h >= t0 ? 0 : (h >= t1 ? 1 : (h >= t2 ? 2 : 3));
-              if (b == pass) { i = c; need = false; }
-            }
-          }
-        }
-      }
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(&A.header[0], (unsigned long long)taken);
+      base = __shfl_sync(FULL, base, 0);
+      int64_t i = (int64_t)base + lane;
+      // hinted order: the k-th problem to start is perm[k] (problems sorted by decreasing hint, crb_mpc_hint_perm_kernel)
+      if (A.perm != nullptr && active && i < A.count) i = (int64_t)__ldg(A.perm + i);
       if (active) {
         if (i < A.count) {
           next = mpc_task_init(sl, T, p, i, A.ld_in, A.x0, A.xref, A.u_init);
@@ -279,7 +237,11 @@ crb_mpc_tasks_kernel(const __grid_constant__ MpcTaskArgs A, const __grid_constan
   }
 }
 
-// histogram of the clamped hints (64 bins, zeroed by the launcher) for mpc_hint_thresholds
+// ---- hinted order: counting sort of the problems by decreasing hint ---------------------------------------------
+// Two small launches in front of the solver: the histogram of the clamped hints, then the scatter - a problem with
+// hint h goes to position (number of problems with a larger hint) + (its arrival rank among the problems with the
+// same hint).  The rank comes from one warp-aggregated atomicAdd per distinct hint value and warp, so the order
+// inside a bin depends on the run; the results do not (a problem's bits do not depend on when it starts).
 __global__ void __launch_bounds__(256) crb_mpc_hint_hist_kernel(int64_t count, const int32_t* __restrict__ hint,
                                                                 unsigned* __restrict__ hist) {
   __shared__ unsigned sh[MPC_HINT_BINS];
@@ -289,6 +251,32 @@ __global__ void __launch_bounds__(256) crb_mpc_hint_hist_kernel(int64_t count, c
     atomicAdd(&sh[mpc_hint_clamp(hint[i])], 1u);
   __syncthreads();
   if (threadIdx.x < MPC_HINT_BINS && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(256) crb_mpc_hint_perm_kernel(int64_t count, const int32_t* __restrict__ hint,
+                                                                const unsigned* __restrict__ hist,
+                                                                unsigned* __restrict__ cursor,
+                                                                int32_t* __restrict__ perm) {
+  __shared__ unsigned first[MPC_HINT_BINS];   // first position of the bin: number of problems with a larger hint
+  if (threadIdx.x < MPC_HINT_BINS) {
+    unsigned f = 0u;
+    for (int b = MPC_HINT_BINS - 1; b > (int)threadIdx.x; --b) f += hist[b];
+    first[threadIdx.x] = f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t rounds = (count + stride - 1) / stride;   // the same trip count for every thread: full-warp intrinsics
+  for (int64_t r = 0; r < rounds; ++r) {
+    const int64_t i = r * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int h = i < count ? mpc_hint_clamp(hint[i]) : -1;
+    const unsigned grp = __match_any_sync(0xffffffffu, h);      // the lanes of this warp with the same hint
+    const int leader = __ffs(grp) - 1;
+    unsigned off = 0u;
+    if (lane == leader && h >= 0) off = atomicAdd(&cursor[h], (unsigned)__popc(grp));
+    off = __shfl_sync(0xffffffffu, off, leader);
+    if (h >= 0) perm[first[h] + off + (unsigned)__popc(grp & lanemask_lt())] = (int32_t)i;
+  }
 }
 
 // Launch geometry for `count` problems of horizon T: warps per CTA, slots per CTA, CTAs, shared memory.
@@ -332,11 +320,16 @@ static bool mpc_tasks_geometry(int sm_count, int T, int64_t count, MpcTaskGeom* 
   return true;
 }
 
-// header (512 B: counters + hint histogram) + slab of stage records + 256 B of alignment slack
+// header (768 B: counters, hint histogram, bin cursors) + slab of stage records + the start order (one int per
+// problem) + 256 B of alignment slack
+#define MPC_TASK_HEADER_BYTES 768
+static size_t mpc_tasks_slab_bytes(const MpcTaskGeom& g, int T) {
+  return ((size_t)g.grid * g.S * (size_t)(T - 1) * MPC_REC * sizeof(float) + 255) & ~(size_t)255;
+}
 size_t crb_mpc_tasks_scratch_bytes(int sm_count, int T, int64_t count) {
   MpcTaskGeom g;
-  if (!mpc_tasks_geometry(sm_count, T, count, &g)) return 768;
-  return 768 + (size_t)g.grid * g.S * (size_t)(T - 1) * MPC_REC * sizeof(float);
+  if (!mpc_tasks_geometry(sm_count, T, count, &g)) return MPC_TASK_HEADER_BYTES + 256;
+  return MPC_TASK_HEADER_BYTES + 256 + mpc_tasks_slab_bytes(g, T) + (size_t)count * sizeof(int32_t);
 }
 
 int crb_mpc_tasks_launch(crb_ctx* ctx, cudaStream_t st, int64_t count, int64_t ld, int T,
@@ -378,15 +371,21 @@ int crb_mpc_tasks_launch(crb_ctx* ctx, cudaStream_t st, int64_t count, int64_t l
   }
   a.x0 = x0; a.xref = xref; a.u_init = u_init;
   a.header = (unsigned long long*)base;
-  a.slab = (float*)(base + 512);
+  a.slab = (float*)(base + MPC_TASK_HEADER_BYTES);
   a.sol = sol; a.u0 = u0; a.cost = cost; a.status = status; a.iters = iters;
-  a.hint = hint;
-  CRB_CUDA(cudaMemsetAsync(base, 0, 512, st));
+  a.perm = nullptr;
+  CRB_CUDA(cudaMemsetAsync(base, 0, MPC_TASK_HEADER_BYTES, st));
   if (hint != nullptr) {
+    int32_t* perm = (int32_t*)(base + MPC_TASK_HEADER_BYTES + mpc_tasks_slab_bytes(g, T));
+    unsigned* hist = (unsigned*)(base + 256);
+    unsigned* cursor = (unsigned*)(base + 512);
     int hg = (int)((count + 2047) / 2048);
     if (hg > 4 * ctx->sm_count) hg = 4 * ctx->sm_count;
-    crb_mpc_hint_hist_kernel<<<hg < 1 ? 1 : hg, 256, 0, st>>>(count, hint, (unsigned*)(base + 256));
-    ctx->launches++;
+    if (hg < 1) hg = 1;
+    crb_mpc_hint_hist_kernel<<<hg, 256, 0, st>>>(count, hint, hist);
+    crb_mpc_hint_perm_kernel<<<hg, 256, 0, st>>>(count, hint, hist, cursor, perm);
+    ctx->launches += 2;
+    a.perm = perm;
   }
   if (bulk)
     crb_mpc_tasks_kernel<true><<<(unsigned)g.grid, g.nwarps * 32, g.smem, st>>>(a, p);

@@ -33,10 +33,6 @@ static uint64_t rng_next(uint64_t* s) {
   return z ^ (z >> 31);
 }
 
-extern "C" void mpc_tasks_sim_hint_thresholds(const unsigned* hist, int64_t n, int* thr) {
-  mpc_hint_thresholds(hist, n, thr);
-}
-
 extern "C" int mpc_tasks_sim_solve(int64_t n, int T, const float* x0, const float* xref, const float* u_init,
                                    const sim_params* prm, float* sol, float* u0, float* cost, int32_t* status,
                                    int32_t* iters, int S, uint64_t seed, int64_t* task_counts /*[3] or NULL*/,
@@ -71,15 +67,16 @@ extern "C" int mpc_tasks_sim_solve(int64_t n, int T, const float* x0, const floa
     return sl;
   };
   for (int s = 0; s < S; ++s) mpc_sw_int(slot_of(s), MPC_SW_PROB) = -1;
-  int64_t next_problem = 0;   // the kernel's global counter (virtual candidates when hints are given)
+  int64_t next_problem = 0;   // the kernel's global counter
   int64_t counts[3] = {0, 0, 0};
-  int hthr[MPC_HINT_PASSES - 1] = {0, 0, 0};
-  int hempty[MPC_HINT_PASSES] = {0, 0, 0, 0};
+  // hinted order: the kernel starts the problems in the order of decreasing (clamped) hint; inside a bin the GPU's
+  // order depends on the run, here it is by index
+  std::vector<int64_t> perm;
   if (hint) {
-    unsigned hist[MPC_HINT_BINS] = {0};
-    for (int64_t i = 0; i < n; ++i) hist[mpc_hint_clamp(hint[i])] += 1u;
-    mpc_hint_thresholds(hist, n, hthr);
-    mpc_hint_empty(hist, hthr, hempty);
+    perm.reserve((size_t)n);
+    for (int b = MPC_HINT_BINS - 1; b >= 0; --b)
+      for (int64_t i = 0; i < n; ++i)
+        if (mpc_hint_clamp(hint[i]) == b) perm.push_back(i);
   }
   uint64_t rs = seed;
   for (;;) {
@@ -106,38 +103,13 @@ extern "C" int mpc_tasks_sim_solve(int64_t n, int T, const float* x0, const floa
         MpcSlot sl = slot_of(q[k]);
         if (mpc_sw_int(sl, MPC_SW_PROB) >= 0) mpc_task_retire(sl, T, p, n, sol, u0, cost, status, iters);
       }
-      // problem indices of the lanes: consecutive ones, or (hinted order) the kernel's claim loop - every round the
-      // lanes that still need a problem claim one candidate each; candidate v is problem v mod n in pass v / n
+      // positions in the start order of the lanes: consecutive; the problem is the position itself or perm[position]
       std::vector<int64_t> pick(take, n);
-      if (!hint) {
-        for (size_t k = 0; k < take; ++k) pick[k] = next_problem + (int64_t)k;
-        next_problem += (int64_t)take;
-      } else {
-        std::vector<char> need(take, 1);
-        for (;;) {
-          int64_t cnt = 0;
-          for (size_t k = 0; k < take; ++k) cnt += need[k];
-          if (cnt == 0) break;
-          int64_t v = next_problem;
-          next_problem += cnt;
-          for (size_t k = 0; k < take; ++k) {
-            if (!need[k]) continue;
-            if (v >= (int64_t)MPC_HINT_PASSES * n) {
-              need[k] = 0;
-            } else {
-              const int pass = (int)(v / n);
-              const int64_t c = v - (int64_t)pass * n;
-              if (hempty[pass]) {   // the kernel's atomicMax: the counter jumps to the end of an empty pass
-                if (next_problem < (int64_t)(pass + 1) * n) next_problem = (int64_t)(pass + 1) * n;
-              } else if (mpc_hint_bucket(hint[c], hthr) == pass) {
-                pick[k] = c;
-                need[k] = 0;
-              }
-            }
-            ++v;
-          }
-        }
+      for (size_t k = 0; k < take; ++k) {
+        const int64_t pos = next_problem + (int64_t)k;
+        if (pos < n) pick[k] = hint ? perm[(size_t)pos] : pos;
       }
+      next_problem += (int64_t)take;
       for (size_t k = 0; k < take; ++k) {
         MpcSlot sl = slot_of(q[k]);
         const int64_t i = pick[k];
