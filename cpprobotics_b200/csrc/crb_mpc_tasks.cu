@@ -237,11 +237,14 @@ crb_mpc_tasks_kernel(const __grid_constant__ MpcTaskArgs A, const __grid_constan
   }
 }
 
-// ---- hinted order: counting sort of the problems by decreasing hint ---------------------------------------------
-// Two small launches in front of the solver: the histogram of the clamped hints, then the scatter - a problem with
-// hint h goes to position (number of problems with a larger hint) + (its arrival rank among the problems with the
-// same hint).  The rank comes from one warp-aggregated atomicAdd per distinct hint value and warp, so the order
-// inside a bin depends on the run; the results do not (a problem's bits do not depend on when it starts).
+// ---- hinted order: the long problems first, the rest in (almost) index order -------------------------------------
+// Two small launches in front of the solver: the histogram of the clamped hints, then the scatter.  The ~15 % of the
+// problems with the largest hints (hint >= thr, mpc_hint_threshold) are sorted by decreasing hint and start first;
+// all the others form ONE bin behind them.  A position is (problems in earlier bins) + (arrival rank in the bin);
+// the rank comes from one warp-aggregated atomicAdd per bin and warp, so the lanes of a warp stay together and the
+// big bin keeps runs of consecutive indices: the solver's refills of those problems still read coalesced rows of
+// x0 / xref.  (A full sort by hint scattered every refill over 32 rows: 4-8 % slower at 2^20 problems, where there
+// is no tail to win back.)  The order inside a bin depends on the run; the results do not.
 __global__ void __launch_bounds__(256) crb_mpc_hint_hist_kernel(int64_t count, const int32_t* __restrict__ hint,
                                                                 unsigned* __restrict__ hist) {
   __shared__ unsigned sh[MPC_HINT_BINS];
@@ -257,10 +260,20 @@ __global__ void __launch_bounds__(256) crb_mpc_hint_perm_kernel(int64_t count, c
                                                                 const unsigned* __restrict__ hist,
                                                                 unsigned* __restrict__ cursor,
                                                                 int32_t* __restrict__ perm) {
-  __shared__ unsigned first[MPC_HINT_BINS];   // first position of the bin: number of problems with a larger hint
+  __shared__ unsigned first[MPC_HINT_BINS];   // first position of the bin: number of problems in earlier bins
+  __shared__ int s_thr;
+  if (threadIdx.x == 0) s_thr = mpc_hint_threshold(hist, count);
+  __syncthreads();
+  const int thr = s_thr;
   if (threadIdx.x < MPC_HINT_BINS) {
+    // bins thr .. 63 in decreasing order, then bin 0 = everything below thr
     unsigned f = 0u;
-    for (int b = MPC_HINT_BINS - 1; b > (int)threadIdx.x; --b) f += hist[b];
+    const int me = (int)threadIdx.x;
+    if (me >= thr) {
+      for (int b = MPC_HINT_BINS - 1; b > me; --b) f += hist[b];
+    } else {
+      for (int b = MPC_HINT_BINS - 1; b >= thr; --b) f += hist[b];
+    }
     first[threadIdx.x] = f;
   }
   __syncthreads();
@@ -269,8 +282,9 @@ __global__ void __launch_bounds__(256) crb_mpc_hint_perm_kernel(int64_t count, c
   const int64_t rounds = (count + stride - 1) / stride;   // the same trip count for every thread: full-warp intrinsics
   for (int64_t r = 0; r < rounds; ++r) {
     const int64_t i = r * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int h = i < count ? mpc_hint_clamp(hint[i]) : -1;
-    const unsigned grp = __match_any_sync(0xffffffffu, h);      // the lanes of this warp with the same hint
+    int h = i < count ? mpc_hint_clamp(hint[i]) : -1;
+    if (h >= 0 && h < thr) h = 0;                               // one bin for everything below the threshold
+    const unsigned grp = __match_any_sync(0xffffffffu, h);      // the lanes of this warp in the same bin
     const int leader = __ffs(grp) - 1;
     unsigned off = 0u;
     if (lane == leader && h >= 0) off = atomicAdd(&cursor[h], (unsigned)__popc(grp));

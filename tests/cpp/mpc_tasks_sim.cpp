@@ -69,14 +69,20 @@ extern "C" int mpc_tasks_sim_solve(int64_t n, int T, const float* x0, const floa
   for (int s = 0; s < S; ++s) mpc_sw_int(slot_of(s), MPC_SW_PROB) = -1;
   int64_t next_problem = 0;   // the kernel's global counter
   int64_t counts[3] = {0, 0, 0};
-  // hinted order: the kernel starts the problems in the order of decreasing (clamped) hint; inside a bin the GPU's
-  // order depends on the run, here it is by index
+  // hinted order: the problems with hint >= thr in the order of decreasing (clamped) hint, then all the others;
+  // inside a bin the GPU's order depends on the run, here it is by index
   std::vector<int64_t> perm;
   if (hint) {
+    unsigned hist[MPC_HINT_BINS] = {0};
+    for (int64_t i = 0; i < n; ++i) hist[mpc_hint_clamp(hint[i])] += 1u;
+    const int thr = mpc_hint_threshold(hist, n);
     perm.reserve((size_t)n);
-    for (int b = MPC_HINT_BINS - 1; b >= 0; --b)
+    for (int b = MPC_HINT_BINS - 1; b >= thr; --b)
       for (int64_t i = 0; i < n; ++i)
         if (mpc_hint_clamp(hint[i]) == b) perm.push_back(i);
+    for (int64_t i = 0; i < n; ++i)
+      if (mpc_hint_clamp(hint[i]) < thr) perm.push_back(i);
+    if ((int64_t)perm.size() != n) return 1;
   }
   uint64_t rs = seed;
   for (;;) {
