@@ -389,7 +389,9 @@ int crb_mpc_tasks_launch(crb_ctx* ctx, cudaStream_t st, int64_t count, int64_t l
   a.sol = sol; a.u0 = u0; a.cost = cost; a.status = status; a.iters = iters;
   a.perm = nullptr;
   CRB_CUDA(cudaMemsetAsync(base, 0, MPC_TASK_HEADER_BYTES, st));
-  if (hint != nullptr) {
+  // With many SM-generations of problems there is no tail to win back and the 15 % scattered refills cost ~3 %
+  // (measured at 2^20 problems): the hints are used up to 6 generations (~170 000 problems on a B200).
+  if (hint != nullptr && count <= 6 * (int64_t)g.grid * g.S) {
     int32_t* perm = (int32_t*)(base + MPC_TASK_HEADER_BYTES + mpc_tasks_slab_bytes(g, T));
     unsigned* hist = (unsigned*)(base + 256);
     unsigned* cursor = (unsigned*)(base + 512);

@@ -873,6 +873,11 @@ def test_pf_sharded_over_two_gpus_equals_the_single_gpu_estimate(engine):
     for p in procs:
         p.join(timeout=60)
     for rank, res, w in got:
-        np.testing.assert_allclose(res[0:21], want[0:21], rtol=1e-9, atol=1e-9)   # same sums, other association
+        # the same sums in another association: the sharded form divides sum(w x) by sum(w), the single-GPU form sums
+        # the normalised weights; narrowed to the reference's float they may differ by one float ulp (xEst) and by
+        # the cancellation in the covariance
+        np.testing.assert_allclose(res[0:4], want[0:4], rtol=2e-7, atol=1e-7)
+        np.testing.assert_allclose(res[4:20], want[4:20], rtol=1e-4, atol=1e-7)
+        np.testing.assert_allclose(res[20], want[20], rtol=1e-9)
         k = n // world
         np.testing.assert_allclose(w, want_w[rank * k:(rank + 1) * k], rtol=1e-6, atol=0)
