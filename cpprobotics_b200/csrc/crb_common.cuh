@@ -32,6 +32,7 @@ struct crb_ctx {
   // device in the same process must set them again, so these are not process-global latches)
   int mpc_tasks_attr_set;
   int ekf_tma_attr_set;
+  int pf_step_attr_set;   // shared-memory carve-out preference of the crb_pf_step kernels (per device)
   int mpc_v0_attr_set;
   unsigned* tickets;      // 64 zeroed words of device memory: "last block finishes the job" counters (kept at zero)
   // NCCL communicator (crb_comm.cu); NULL = single GPU
