@@ -646,9 +646,10 @@ def bench_pf_iteration(eng, rank, world, steps, warmup):
                 timing=timing_record(steps),
                 config=dict(workload="pf_full_iteration_2^20_particles_per_gpu (crb_pf_step)", steps=steps,
                             resampled_last_step=bool(r[22] == 1.0), neff_last_step=float(r[21]), launch=mode,
-                            note="4 kernels per iteration (predict+weight, moments, normalise+scan with the combine in "
-                                 "its prologue, gather with the block-offset scan and the decision in its prologue), "
-                                 "programmatic dependent launch, no host synchronisation, no device copy; round 1 "
+                            note="3 kernels per iteration (predict+weight leaving the CTA weight sums; normalise + scan + "
+                                 "moments of the normalised weights; gather with the block-offset scan and the resampling "
+                                 "decision in its prologue and one extra CTA for xEst / PEst), programmatic dependent "
+                                 "launch, no host synchronisation, no device copy; round 1 "
                                  "was 10 kernels, 2 synchronous read-backs and a 16 MB copy (135 us)"))
 
 

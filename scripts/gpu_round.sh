@@ -7,7 +7,7 @@ mkdir -p $OUT
 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_gpu_$TAG.log
 python bench.py --steps 20 --warmup 5 > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err
 NCU="ncu --clock-control none"
-$NCU --metrics gpu__time_duration.sum -c 400 --csv --log-file $OUT/launches_$TAG.csv \
+$NCU --metrics gpu__time_duration.sum -c 1200 --csv --log-file $OUT/launches_$TAG.csv \
     python bench.py --steps 5 --warmup 3 --no-cpu > $OUT/launches_$TAG.stdout 2>&1
 for w in ekf pf mpc; do
   case $w in ekf) K=crb_ekf_step_kernel;; pf) K=crb_pf_predict_weight_lean_kernel;; mpc) K=crb_mpc_tasks_kernel;; esac

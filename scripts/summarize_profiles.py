@@ -48,8 +48,8 @@ def launches(tag):
         cnt[k] += 1
     total = sum(tot.values())
     out = [f"# {tag} — ncu launch list of `python bench.py --steps 5 --warmup 3 --no-cpu` (all workloads)", "",
-           "`ncu --metrics gpu__time_duration.sum --clock-control none -c 400` (cold-cache, serialised: compare "
-           "shares, not absolutes).", f"Raw CSV: gpurun_out/launches_{tag}.csv (first 400 launches).", "",
+           "`ncu --metrics gpu__time_duration.sum --clock-control none -c 1200` (cold-cache, serialised: compare "
+           "shares, not absolutes).", f"Raw CSV: gpurun_out/launches_{tag}.csv (first 1200 launches).", "",
            "| kernel | launches | total us | share | avg us |", "|---|---|---|---|---|"]
     for k, v in tot.most_common():
         out.append(f"| `{k}` | {cnt[k]} | {v:.1f} | {100 * v / total:.1f} % | {v / cnt[k]:.2f} |")
