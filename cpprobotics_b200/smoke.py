@@ -74,5 +74,34 @@ def run() -> None:
     print(f"smoke MPC   n={nm} T={T}: bit-identical to the oracle; mean iters "
           f"{iters.float().mean().item():.2f}, converged+stationary "
           f"{int(((status == 0) | (status == 2)).sum().item())}/{nm}")
+    # the same solve started in hinted order (the previous solve's iteration counts): the same bits
+    sol2, u02, cost2 = torch.empty_like(sol), torch.empty_like(u0), torch.empty_like(cost)
+    status2, iters2 = torch.empty_like(status), torch.empty_like(iters)
+    eng.mpc_solve_hinted(std, xrd, T, iters, prm, sol=sol2, u0=u02, cost=cost2, status=status2, iters=iters2)
+    torch.cuda.synchronize()
+    assert (torch.equal(sol2, sol) and torch.equal(u02, u0) and torch.equal(cost2, cost)
+            and torch.equal(status2, status) and torch.equal(iters2, iters)), "hinted MPC solve changed the result"
+    print("smoke MPC   hinted order: bit-identical to the index-order solve")
+
+    # one whole particle-filter iteration on the device (crb_pf_step) against the oracle's stages
+    npf = 8192
+    px, pw, noise = synth.pf_inputs(npf)
+    uni = (1.0 + np.random.default_rng(7).random(npf)).astype(np.float32)
+    pxd, pwd, nd, ud2 = (torch.from_numpy(a).to(dev) for a in (px, pw, noise, uni))
+    nxt = torch.empty_like(pxd)
+    res_d = eng.pf_step(pxd, pwd, nxt, nd, lm, uniforms=ud2, nth=float(npf))
+    torch.cuda.synchronize()
+    res = res_d.cpu().numpy()
+    pxo, pwo = O.pf_predict_weight_batched(px, pw, noise, lm)
+    pwn, xeo, Peo, swo = O.pf_estimate(pxo, pwo)
+    assert res[22] == 1.0 and abs(res[20] - swo) <= 1e-5 * abs(swo), (res[20], swo)
+    assert np.allclose(res[0:4], xeo, rtol=1e-5, atol=1e-5), (res[0:4], xeo)
+    w_out = pwd.cpu().numpy()
+    assert np.all(w_out == np.float32(1.0 / npf)), "resampled weights are not uniform"
+    src = pxd.cpu().numpy()
+    got = nxt.cpu().numpy()
+    keys = {tuple(c) for c in src.T}
+    assert all(tuple(c) in keys for c in got.T[:: max(1, npf // 256)]), "a resampled particle is not a copy of an input"
+    print(f"smoke PF    full iteration n={npf}: sum_w / xEst match the oracle, particles resampled on the device")
     print(f"smoke ok: {eng.launches} kernel launches through libcrb.so")
     eng.close()
